@@ -1,0 +1,168 @@
+/* r433b.h -- C ABI of the B200 IQ -> pulse-train -> bitbuffer hot path.
+ *
+ * This is the seam a maintainer of merbanan/rtl_433 binds instead of the per-block calls that
+ * push_sdr_flow() makes today (src/r_flow.c:151-161, :198, :206-208, :243, :259, :302):
+ *
+ *   envelope_detect / magnitude_est_cu8 / magnitude_est_cs16   src/baseband.c:36,65,96
+ *   baseband_low_pass_filter                                   src/baseband.c:145
+ *   baseband_demod_FM / baseband_demod_FM_cs16                 src/baseband.c:210,303
+ *   pulse_detect_package (+ pulse_detect_fsk_*)                src/pulse_detect.c:199
+ *   pulse_slicer_{pcm,ppm,pwm,manchester_zerobit,dmc,piwm_raw,piwm_dc,nrzs,osv1,rzi}
+ *                                                              src/pulse_slicer.c:68-918
+ *   run_ook_demods / run_fsk_demods / account_event            src/r_api.c:438-550, src/pulse_slicer.c:26
+ *
+ * Plain C, plain pointers and sizes; no CUDA or torch types.  One context per GPU, not
+ * thread-safe (the reference's decoders are not re-entrant either).  Every function returns
+ * 0 on success or a negative R433B_E* code; r433b_last_error() explains the last failure.
+ * There is NO CPU fallback: without a usable CUDA device r433b_create() fails.
+ */
+#ifndef R433B_H_
+#define R433B_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define R433B_OK 0
+#define R433B_EINVAL (-1)   /* bad argument */
+#define R433B_ECUDA (-2)    /* CUDA runtime error, see r433b_last_error() */
+#define R433B_ENOMEM (-3)   /* host or device allocation failed */
+#define R433B_EOVERFLOW (-4) /* a result arena was too small even after regrowth */
+#define R433B_ESTATE (-5)   /* call sequence error (e.g. fetch before process) */
+
+#define R433B_FMT_CU8 2  /* bytes per IQ sample; dm_state.sample_size, include/r_private.h:39 */
+#define R433B_FMT_CS16 4
+
+#define R433B_FPDM_CLASSIC 0 /* FSK_PULSE_DETECT_OLD,  include/pulse_detect.h:29-34 */
+#define R433B_FPDM_MINMAX 1  /* FSK_PULSE_DETECT_NEW  */
+#define R433B_FPDM_AUTO 2    /* by centre frequency, src/rtl_433.c:1094-1102 */
+
+#define R433B_PACKAGE_OOK 1 /* enum package_types, include/pulse_detect.h:23-26 */
+#define R433B_PACKAGE_FSK 2
+
+typedef struct r433b_ctx r433b_ctx;
+
+/* Slicer-relevant part of an r_device (include/r_device.h:59-72). */
+typedef struct r433b_device {
+    uint32_t modulation;
+    float short_width, long_width, reset_limit, gap_limit, sync_width, tolerance;
+    uint32_t priority;
+} r433b_device;
+
+/* One batch of capture "files" (all of one format / rate / centre frequency).
+   Stream i occupies bytes [offsets[i], offsets[i+1]) of `data`; offsets must be multiples
+   of 16.  `data` is host memory (pageable or pinned) or, with data_on_device, device memory. */
+typedef struct r433b_batch {
+    void const *data;
+    uint64_t const *offsets; /* n_streams + 1 entries, host memory */
+    uint32_t n_streams;
+    uint32_t sample_format;  /* R433B_FMT_* */
+    uint32_t samp_rate;      /* Hz */
+    uint32_t center_frequency; /* Hz */
+    uint32_t fpdm_mode;      /* R433B_FPDM_* */
+    uint32_t block_bytes;    /* 0 = 262144, the reference's DEFAULT_BUF_LENGTH */
+    int32_t data_on_device;
+    int32_t want_stages;     /* keep the AM/FM stage arrays on the device for r433b_copy_stage() */
+} r433b_batch;
+
+/* A detected package = the integer part of pulse_data_t (include/pulse_data.h:30-50) plus
+   where it was returned.  pulse/gap widths live in the pools at [pulse_off, +pulse_count). */
+typedef struct r433b_package {
+    uint32_t stream;
+    uint32_t seq;          /* order within the stream */
+    int32_t type;          /* R433B_PACKAGE_* */
+    int32_t block;         /* index of the reference block that returned it; n_blocks = flush */
+    uint64_t offset;
+    uint64_t end_pos;      /* absolute sample index at which it was returned */
+    uint32_t start_ago, end_ago, num_pulses;
+    uint32_t pulse_off, pulse_count;
+    int32_t ook_low_estimate, ook_high_estimate, fsk_f1_est, fsk_f2_est;
+    uint32_t first_pair;   /* index of this package's device 0 in the pair table */
+} r433b_package;
+
+/* One (package, device) slicer run.  Its events are `bytes` bytes at `offset` of the event arena. */
+typedef struct r433b_pair {
+    uint64_t offset;
+    uint32_t bytes;
+    uint32_t events;
+} r433b_pair;
+
+/* Host view of a processed batch; pointers stay valid until the next r433b_process(). */
+typedef struct r433b_results {
+    uint32_t n_packages;
+    uint32_t n_devices;
+    r433b_package const *packages; /* sorted by (stream, seq) */
+    int32_t const *pulse_pool;
+    int32_t const *gap_pool;
+    r433b_pair const *pairs;       /* n_packages * n_devices, row = package */
+    uint8_t const *events;         /* event arena */
+    uint64_t event_bytes;
+    uint64_t n_events;
+    uint64_t n_samples;            /* IQ samples consumed */
+} r433b_results;
+
+/* Wall/device timing of the last r433b_process(), milliseconds. */
+typedef struct r433b_timing {
+    float h2d_ms, detect_ms, slice_ms, d2h_ms, total_ms;
+    uint32_t detect_launches, slice_launches;
+} r433b_timing;
+
+int r433b_create(int cuda_device, r433b_ctx **out);
+void r433b_destroy(r433b_ctx *ctx);
+char const *r433b_last_error(r433b_ctx const *ctx);
+
+/* pulse_detect_set_levels(), src/pulse_detect.c:86; defaults 0, 0.0, -12.1442, 9.0 (src/r_api.c:153-155) */
+int r433b_set_levels(r433b_ctx *ctx, int use_mag_est, float level_limit_db, float min_level_db, float min_snr_db);
+/* -Y filter / dm_state.fm_low_pass; 0 = automatic (src/r_flow.c:204) */
+int r433b_set_fm_low_pass(r433b_ctx *ctx, float fm_low_pass);
+
+/* The registered decoder list in registration order (cfg->demod->r_devs, src/r_api.c:267). */
+int r433b_set_devices(r433b_ctx *ctx, r433b_device const *devs, uint32_t n);
+/* Same, reading the fields out of the reference's own `r_device` structs. */
+struct r_device;
+int r433b_set_r_devices(r433b_ctx *ctx, struct r_device *const *devs, uint32_t n);
+
+/* rtl_433 -r on every stream of the batch: block loop, flush, reset (src/rtl_433.c:1797-1854),
+   then all slicers on every package.  Synchronous; results stay on the device until fetched. */
+int r433b_process(r433b_ctx *ctx, r433b_batch const *batch);
+/* Copy the compact results to host memory owned by the context. */
+int r433b_fetch(r433b_ctx *ctx, r433b_results *out);
+int r433b_get_timing(r433b_ctx const *ctx, r433b_timing *out);
+/* Counters available right after r433b_process() without a fetch: packages, events, event bytes. */
+int r433b_get_counts(r433b_ctx const *ctx, uint64_t out[4]);
+
+/* Stage arrays of one stream (batch.want_stages): what dm_state.am_buf / buf.fm held. */
+int r433b_copy_stage(r433b_ctx *ctx, uint32_t stream, int16_t *am, int16_t *fm, uint64_t max_samples);
+
+/* ---- host-side replay: the part of run_*_demods()/account_event() that stays on the CPU ---- */
+
+struct bitbuffer;
+struct pulse_data;
+
+/* Re-inflate event `index` (0-based within its pair) into a caller-owned bitbuffer_t. */
+int r433b_event_to_bitbuffer(uint8_t const *pair_events, uint32_t pair_bytes, uint32_t index,
+        struct bitbuffer *out, uint32_t *consumed);
+/* Fill a caller-owned pulse_data_t (incl. calc_rssi_snr(), src/r_flow.c:35-64) for one package. */
+int r433b_package_to_pulse_data(r433b_ctx const *ctx, r433b_results const *res, uint32_t package,
+        struct pulse_data *out);
+/* float sample_file_pos of the block that returned the package (src/rtl_433.c:1839) */
+float r433b_package_file_pos(r433b_ctx const *ctx, r433b_results const *res, uint32_t package);
+
+/* Called once per event in the reference's order: package -> priority class -> registration
+   order -> event order.  Return value is the decoder's (account_event's `ret`); > 0 in a
+   priority class stops later classes of that package (src/r_api.c:444). */
+typedef int (*r433b_event_fn)(void *user, uint32_t package, uint32_t device, struct pulse_data const *pd,
+        struct bitbuffer *bits);
+int r433b_dispatch(r433b_ctx *ctx, r433b_results const *res, uint32_t stream, r433b_event_fn fn, void *user);
+/* Same with the real r_device list: calls decode_fn and keeps the per-decoder statistics
+   exactly as account_event() does (src/pulse_slicer.c:26-66). */
+int r433b_dispatch_r_devices(r433b_ctx *ctx, r433b_results const *res, uint32_t stream,
+        struct r_device *const *devs, uint32_t n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* R433B_H_ */

@@ -1,0 +1,622 @@
+// r433b_api.cu -- the C ABI declared in include/r433b.h: context, batch processing on the GPU,
+// result fetch, and the CPU-side replay that feeds events to decoders in the reference's order.
+// There is no CPU implementation of the DSP here: every sample goes through k_detect/k_slice.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/r433b.h"
+#include "../../include/r433b_abi.h"
+#include "r433b_kernels.cuh"
+#include "r433b_host.hpp"
+
+using namespace r433b;
+
+static_assert(sizeof(struct bitbuffer) == 6604, "bitbuffer_t layout");
+static_assert(sizeof(struct pulse_data) == 9672, "pulse_data_t layout");
+static_assert(sizeof(struct r_device) == 152, "r_device layout");
+static_assert(offsetof(struct bitbuffer, bb) == 204, "bitbuffer_t.bb offset");
+
+namespace {
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+};
+
+struct HostBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+};
+
+} // namespace
+
+struct r433b_ctx {
+    int device = 0;
+    std::string err;
+    // detector / demod configuration
+    int use_mag = 0;
+    float level_limit = 0.0f, min_level = -12.1442f, min_snr = 9.0f, fm_low_pass = 0.0f;
+    std::vector<r433b_device> devs;
+    // last batch (kept for the host replay)
+    r433b_batch batch{};
+    std::vector<uint64_t> offsets;
+    bool processed = false, fetched = false;
+    unsigned fpdm = 0;
+    int enable_fm = 0;
+    Levels lv{};
+    // device memory (grow only)
+    DevBuf d_data, d_offsets, d_train, d_pkgs, d_ppool, d_gpool, d_counters, d_am, d_fm;
+    DevBuf d_devparams, d_lists, d_pairs, d_arena, d_cursor;
+    size_t pkg_cap = 0, pool_cap = 0, arena_cap = 0;
+    unsigned n_ook = 0, n_fsk = 0;
+    // counts of the last batch
+    unsigned n_pkgs = 0, pool_used = 0;
+    unsigned long long event_bytes = 0, n_events = 0, n_samples = 0;
+    // pinned host result buffers
+    HostBuf h_pkgs, h_ppool, h_gpool, h_pairs, h_events, h_small;
+    r433b_timing timing{};
+    cudaEvent_t ev[6]{};
+};
+
+namespace {
+
+int fail(r433b_ctx *c, int code, char const *what, cudaError_t e = cudaSuccess)
+{
+    if (c) {
+        c->err = what;
+        if (e != cudaSuccess) {
+            c->err += ": ";
+            c->err += cudaGetErrorString(e);
+        }
+    }
+    return code;
+}
+
+#define CU(call)                                                   \
+    do {                                                           \
+        cudaError_t e_ = (call);                                   \
+        if (e_ != cudaSuccess) return fail(ctx, R433B_ECUDA, #call, e_); \
+    } while (0)
+
+int dev_reserve(r433b_ctx *ctx, DevBuf &b, size_t bytes)
+{
+    if (bytes <= b.cap) return 0;
+    if (b.p) cudaFree(b.p);
+    b.p = nullptr;
+    b.cap = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&b.p, want);
+    if (e != cudaSuccess) return fail(ctx, R433B_ENOMEM, "cudaMalloc", e);
+    b.cap = want;
+    return 0;
+}
+
+int host_reserve(r433b_ctx *ctx, HostBuf &b, size_t bytes)
+{
+    if (bytes <= b.cap) return 0;
+    if (b.p) cudaFreeHost(b.p);
+    b.p = nullptr;
+    b.cap = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMallocHost(&b.p, want);
+    if (e != cudaSuccess) return fail(ctx, R433B_ENOMEM, "cudaMallocHost", e);
+    b.cap = want;
+    return 0;
+}
+
+} // namespace
+
+extern "C" {
+
+int r433b_create(int cuda_device, r433b_ctx **out)
+{
+    if (!out) return R433B_EINVAL;
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0 || cuda_device < 0 || cuda_device >= n) {
+        fprintf(stderr, "r433b_create: no usable CUDA device %d (%s); there is no CPU fallback\n", cuda_device,
+                e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0 or index out of range");
+        return R433B_ECUDA;
+    }
+    r433b_ctx *ctx = new (std::nothrow) r433b_ctx();
+    if (!ctx) return R433B_ENOMEM;
+    ctx->device = cuda_device;
+    if (cudaSetDevice(cuda_device) != cudaSuccess) {
+        delete ctx;
+        return R433B_ECUDA;
+    }
+    for (auto &v : ctx->ev) cudaEventCreate(&v);
+    ctx->lv = compute_levels(0, 0.0f, -12.1442f, 9.0f);
+    *out = ctx;
+    return R433B_OK;
+}
+
+void r433b_destroy(r433b_ctx *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    for (DevBuf *b : {&ctx->d_data, &ctx->d_offsets, &ctx->d_train, &ctx->d_pkgs, &ctx->d_ppool, &ctx->d_gpool,
+                 &ctx->d_counters, &ctx->d_am, &ctx->d_fm, &ctx->d_devparams, &ctx->d_lists, &ctx->d_pairs,
+                 &ctx->d_arena, &ctx->d_cursor})
+        if (b->p) cudaFree(b->p);
+    for (HostBuf *b : {&ctx->h_pkgs, &ctx->h_ppool, &ctx->h_gpool, &ctx->h_pairs, &ctx->h_events, &ctx->h_small})
+        if (b->p) cudaFreeHost(b->p);
+    for (auto &v : ctx->ev)
+        if (v) cudaEventDestroy(v);
+    delete ctx;
+}
+
+char const *r433b_last_error(r433b_ctx const *ctx) { return ctx ? ctx->err.c_str() : "no context"; }
+
+int r433b_set_levels(r433b_ctx *ctx, int use_mag_est, float level_limit_db, float min_level_db, float min_snr_db)
+{
+    if (!ctx) return R433B_EINVAL;
+    ctx->use_mag = use_mag_est ? 1 : 0;
+    ctx->level_limit = level_limit_db;
+    ctx->min_level = min_level_db;
+    ctx->min_snr = min_snr_db;
+    ctx->lv = compute_levels(ctx->use_mag, level_limit_db, min_level_db, min_snr_db);
+    return R433B_OK;
+}
+
+int r433b_set_fm_low_pass(r433b_ctx *ctx, float v)
+{
+    if (!ctx) return R433B_EINVAL;
+    ctx->fm_low_pass = v;
+    return R433B_OK;
+}
+
+int r433b_set_devices(r433b_ctx *ctx, r433b_device const *devs, uint32_t n)
+{
+    if (!ctx || (n && !devs)) return R433B_EINVAL;
+    ctx->devs.assign(devs, devs + n);
+    return R433B_OK;
+}
+
+int r433b_set_r_devices(r433b_ctx *ctx, struct r_device *const *devs, uint32_t n)
+{
+    if (!ctx || (n && !devs)) return R433B_EINVAL;
+    ctx->devs.resize(n);
+    for (uint32_t i = 0; i < n; ++i) {
+        struct r_device const *d = devs[i];
+        r433b_device &o = ctx->devs[i];
+        o.modulation = d->modulation;
+        o.short_width = d->short_width;
+        o.long_width = d->long_width;
+        o.reset_limit = d->reset_limit;
+        o.gap_limit = d->gap_limit;
+        o.sync_width = d->sync_width;
+        o.tolerance = d->tolerance;
+        o.priority = d->priority;
+    }
+    return R433B_OK;
+}
+
+int r433b_process(r433b_ctx *ctx, r433b_batch const *b)
+{
+    if (!ctx || !b || !b->offsets || (b->n_streams && !b->data)) return fail(ctx, R433B_EINVAL, "null argument");
+    if (b->sample_format != R433B_FMT_CU8 && b->sample_format != R433B_FMT_CS16)
+        return fail(ctx, R433B_EINVAL, "sample_format must be 2 (cu8) or 4 (cs16)");
+    if (b->samp_rate == 0) return fail(ctx, R433B_EINVAL, "samp_rate is 0");
+    int const SS = (int)b->sample_format;
+    uint32_t block_bytes = b->block_bytes ? b->block_bytes : 262144u;
+    int const T = SS == 2 ? TileCfg<2>::T : TileCfg<4>::T;
+    if (block_bytes % (uint32_t)(T * SS) != 0) return fail(ctx, R433B_EINVAL, "block_bytes must be a multiple of 2048");
+    for (uint32_t i = 0; i <= b->n_streams; ++i) {
+        if (b->offsets[i] % 16) return fail(ctx, R433B_EINVAL, "stream offsets must be multiples of 16 bytes");
+        if (i && b->offsets[i] < b->offsets[i - 1]) return fail(ctx, R433B_EINVAL, "offsets not ascending");
+    }
+    CU(cudaSetDevice(ctx->device));
+    ctx->processed = ctx->fetched = false;
+    ctx->batch = *b;
+    ctx->batch.block_bytes = block_bytes;
+    ctx->offsets.assign(b->offsets, b->offsets + b->n_streams + 1);
+    ctx->batch.offsets = ctx->offsets.data();
+    uint64_t const total_bytes = b->n_streams ? b->offsets[b->n_streams] : 0;
+    uint32_t const n_devs = (uint32_t)ctx->devs.size();
+
+    // src/rtl_433.c:1094-1102 and :1515-1522
+    ctx->fpdm = b->fpdm_mode == R433B_FPDM_AUTO ? (b->center_frequency > 800000000u ? 1u : 0u) : b->fpdm_mode;
+    ctx->enable_fm = 0;
+    for (auto const &d : ctx->devs)
+        if (d.modulation >= 16) ctx->enable_fm = 1;
+
+    cudaStream_t const st = 0;
+    CU(cudaEventRecord(ctx->ev[0], st));
+
+    // ---- inputs ---------------------------------------------------------------------
+    uint8_t const *d_in;
+    if (b->data_on_device) {
+        d_in = (uint8_t const *)b->data;
+    } else {
+        if (int r = dev_reserve(ctx, ctx->d_data, total_bytes + 64)) return r;
+        if (total_bytes) CU(cudaMemcpyAsync(ctx->d_data.p, b->data, total_bytes, cudaMemcpyHostToDevice, st));
+        d_in = (uint8_t const *)ctx->d_data.p;
+    }
+    if (int r = dev_reserve(ctx, ctx->d_offsets, (b->n_streams + 1) * sizeof(uint64_t))) return r;
+    CU(cudaMemcpyAsync(ctx->d_offsets.p, ctx->offsets.data(), (b->n_streams + 1) * sizeof(uint64_t),
+            cudaMemcpyHostToDevice, st));
+    CU(cudaEventRecord(ctx->ev[1], st));
+
+    if (int r = dev_reserve(ctx, ctx->d_train, (size_t)std::max(1u, b->n_streams) * kTrainInts * sizeof(int))) return r;
+    if (int r = dev_reserve(ctx, ctx->d_counters, 64)) return r;
+    if (b->want_stages) {
+        if (int r = dev_reserve(ctx, ctx->d_am, total_bytes / SS * sizeof(int16_t) + 16)) return r;
+        if (int r = dev_reserve(ctx, ctx->d_fm, total_bytes / SS * sizeof(int16_t) + 16)) return r;
+    }
+
+    DetectParams dp{};
+    dp.data = d_in;
+    dp.offsets = (unsigned long long const *)ctx->d_offsets.p;
+    dp.n_streams = b->n_streams;
+    dp.use_mag = ctx->use_mag;
+    dp.enable_fm = ctx->enable_fm;
+    dp.fpdm = (int)ctx->fpdm;
+    dp.rate = b->samp_rate;
+    dp.block_samples = block_bytes / SS;
+    dp.lv = ctx->lv;
+    dp.lpf_a1 = ((int)(0.85408 * 32768)) >> 1; // src/baseband.c:151-152
+    dp.lpf_b0 = ((int)(0.07296 * 32768)) >> 1;
+    dp.fm_a1 = dp.fm_b0 = 0;
+    dp.wrap_free = 1;
+    if (ctx->enable_fm) {
+        float lp = ctx->fm_low_pass != 0.0f ? ctx->fm_low_pass : ctx->fpdm ? 0.2f : 0.1f; // src/r_flow.c:204
+        fm_coeffs(SS == 4, b->samp_rate, lp, dp.fm_a1, dp.fm_b0);
+        long long unity = SS == 2 ? 16384ll : (1ll << 30);
+        dp.wrap_free = dp.fm_a1 >= 0 && dp.fm_b0 >= 0 && (long long)dp.fm_a1 + 2ll * dp.fm_b0 <= unity;
+    }
+    dp.train_scratch = (int *)ctx->d_train.p;
+    dp.counters = (unsigned *)ctx->d_counters.p;
+    dp.am_out = b->want_stages ? (int16_t *)ctx->d_am.p : nullptr;
+    dp.fm_out = b->want_stages ? (int16_t *)ctx->d_fm.p : nullptr;
+
+    if (ctx->pkg_cap < (size_t)b->n_streams * 16 + 1024) ctx->pkg_cap = (size_t)b->n_streams * 16 + 1024;
+    if (ctx->pool_cap < ctx->pkg_cap * 128) ctx->pool_cap = ctx->pkg_cap * 128;
+
+    unsigned detect_launches = 0;
+    unsigned counters[4] = {0, 0, 0, 0};
+    for (int attempt = 0; attempt < 3; ++attempt) {
+        if (int r = dev_reserve(ctx, ctx->d_pkgs, ctx->pkg_cap * sizeof(r433b_package))) return r;
+        if (int r = dev_reserve(ctx, ctx->d_ppool, ctx->pool_cap * sizeof(int))) return r;
+        if (int r = dev_reserve(ctx, ctx->d_gpool, ctx->pool_cap * sizeof(int))) return r;
+        dp.pkgs = (r433b_package *)ctx->d_pkgs.p;
+        dp.pkg_cap = (unsigned)std::min<size_t>(ctx->pkg_cap, 0xffffffffu);
+        dp.pulse_pool = (int *)ctx->d_ppool.p;
+        dp.gap_pool = (int *)ctx->d_gpool.p;
+        dp.pool_cap = (unsigned)std::min<size_t>(ctx->pool_cap, 0xffffffffu);
+        CU(cudaMemsetAsync(ctx->d_counters.p, 0, 64, st));
+        if (b->n_streams) {
+            unsigned grid = (b->n_streams + kDetectWarps - 1) / kDetectWarps;
+            if (SS == 2) {
+                size_t sm = (size_t)kDetectWarps * 2 * TileCfg<2>::kTileHalf * sizeof(int16_t);
+                k_detect<2><<<grid, kDetectWarps * 32, sm, st>>>(dp);
+            } else {
+                size_t sm = (size_t)kDetectWarps * 2 * TileCfg<4>::kTileHalf * sizeof(int16_t);
+                k_detect<4><<<grid, kDetectWarps * 32, sm, st>>>(dp);
+            }
+            CU(cudaGetLastError());
+            detect_launches++;
+        }
+        CU(cudaMemcpyAsync(counters, ctx->d_counters.p, sizeof(counters), cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        if (!counters[2]) break;
+        // arenas were too small: the counters hold the true need
+        ctx->pkg_cap = std::max<size_t>(ctx->pkg_cap, (size_t)counters[0] + 64);
+        ctx->pool_cap = std::max<size_t>(ctx->pool_cap, (size_t)counters[1] + 4096);
+        if (attempt == 2) return fail(ctx, R433B_EOVERFLOW, "package arena overflow");
+    }
+    ctx->n_pkgs = counters[0];
+    ctx->pool_used = counters[1];
+    CU(cudaEventRecord(ctx->ev[2], st));
+
+    // ---- slicers ----------------------------------------------------------------------
+    std::vector<SlicerParams> sp(n_devs);
+    std::vector<unsigned> ook, fsk;
+    for (uint32_t i = 0; i < n_devs; ++i) sp[i] = scale_device(ctx->devs[i], b->samp_rate);
+    for (uint32_t i = 0; i < n_devs; ++i) {
+        if (device_takes((int)ctx->devs[i].modulation, 1)) ook.push_back(i);
+        if (device_takes((int)ctx->devs[i].modulation, 2)) fsk.push_back(i);
+    }
+    auto by_mod = [&](unsigned a, unsigned c) {
+        if (ctx->devs[a].modulation != ctx->devs[c].modulation) return ctx->devs[a].modulation < ctx->devs[c].modulation;
+        return a < c;
+    };
+    std::sort(ook.begin(), ook.end(), by_mod);
+    std::sort(fsk.begin(), fsk.end(), by_mod);
+    ctx->n_ook = (unsigned)ook.size();
+    ctx->n_fsk = (unsigned)fsk.size();
+
+    unsigned long long cursor[4] = {0, 0, 0, 0};
+    unsigned slice_launches = 0;
+    if (ctx->n_pkgs && n_devs) {
+        if (int r = dev_reserve(ctx, ctx->d_devparams, n_devs * sizeof(SlicerParams))) return r;
+        if (int r = dev_reserve(ctx, ctx->d_lists, (ook.size() + fsk.size() + 1) * sizeof(unsigned))) return r;
+        if (int r = dev_reserve(ctx, ctx->d_cursor, 64)) return r;
+        CU(cudaMemcpyAsync(ctx->d_devparams.p, sp.data(), n_devs * sizeof(SlicerParams), cudaMemcpyHostToDevice, st));
+        if (!ook.empty())
+            CU(cudaMemcpyAsync(ctx->d_lists.p, ook.data(), ook.size() * sizeof(unsigned), cudaMemcpyHostToDevice, st));
+        if (!fsk.empty())
+            CU(cudaMemcpyAsync((unsigned *)ctx->d_lists.p + ook.size(), fsk.data(), fsk.size() * sizeof(unsigned),
+                    cudaMemcpyHostToDevice, st));
+        size_t pair_bytes = (size_t)ctx->n_pkgs * n_devs * sizeof(r433b_pair);
+        if (int r = dev_reserve(ctx, ctx->d_pairs, pair_bytes)) return r;
+        if (ctx->arena_cap < total_bytes / 2 + (1u << 20)) ctx->arena_cap = total_bytes / 2 + (1u << 20);
+        for (int attempt = 0; attempt < 3; ++attempt) {
+            if (int r = dev_reserve(ctx, ctx->d_arena, ctx->arena_cap)) return r;
+            CU(cudaMemsetAsync(ctx->d_pairs.p, 0, pair_bytes, st));
+            CU(cudaMemsetAsync(ctx->d_cursor.p, 0, 64, st));
+            SliceParams q{};
+            q.pkgs = (r433b_package *)ctx->d_pkgs.p;
+            q.n_pkgs = ctx->n_pkgs;
+            q.pulse_pool = (int const *)ctx->d_ppool.p;
+            q.gap_pool = (int const *)ctx->d_gpool.p;
+            q.dev = (SlicerParams const *)ctx->d_devparams.p;
+            q.n_devs = n_devs;
+            q.ook_list = (unsigned const *)ctx->d_lists.p;
+            q.fsk_list = (unsigned const *)ctx->d_lists.p + ook.size();
+            q.n_ook = ctx->n_ook;
+            q.n_fsk = ctx->n_fsk;
+            q.pairs = (r433b_pair *)ctx->d_pairs.p;
+            q.arena = (uint8_t *)ctx->d_arena.p;
+            q.arena_cap = ctx->arena_cap;
+            q.cursor = (unsigned long long *)ctx->d_cursor.p;
+            k_slice<<<ctx->n_pkgs, kSliceThreads, 0, st>>>(q);
+            CU(cudaGetLastError());
+            slice_launches++;
+            CU(cudaMemcpyAsync(cursor, ctx->d_cursor.p, sizeof(cursor), cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+            if (!cursor[2]) break;
+            ctx->arena_cap = (size_t)cursor[0] + (1u << 20);
+            if (attempt == 2) return fail(ctx, R433B_EOVERFLOW, "event arena overflow");
+        }
+    }
+    ctx->event_bytes = cursor[0];
+    ctx->n_events = cursor[1];
+    ctx->n_samples = total_bytes / SS;
+    CU(cudaEventRecord(ctx->ev[3], st));
+    CU(cudaEventSynchronize(ctx->ev[3]));
+    cudaEventElapsedTime(&ctx->timing.h2d_ms, ctx->ev[0], ctx->ev[1]);
+    cudaEventElapsedTime(&ctx->timing.detect_ms, ctx->ev[1], ctx->ev[2]);
+    cudaEventElapsedTime(&ctx->timing.slice_ms, ctx->ev[2], ctx->ev[3]);
+    cudaEventElapsedTime(&ctx->timing.total_ms, ctx->ev[0], ctx->ev[3]);
+    ctx->timing.d2h_ms = 0;
+    ctx->timing.detect_launches = detect_launches;
+    ctx->timing.slice_launches = slice_launches;
+    ctx->processed = true;
+    return R433B_OK;
+}
+
+int r433b_get_counts(r433b_ctx const *ctx, uint64_t out[4])
+{
+    if (!ctx || !out) return R433B_EINVAL;
+    if (!ctx->processed) return R433B_ESTATE;
+    out[0] = ctx->n_pkgs;
+    out[1] = ctx->n_events;
+    out[2] = ctx->event_bytes;
+    out[3] = ctx->n_samples;
+    return R433B_OK;
+}
+
+int r433b_get_timing(r433b_ctx const *ctx, r433b_timing *out)
+{
+    if (!ctx || !out) return R433B_EINVAL;
+    *out = ctx->timing;
+    return R433B_OK;
+}
+
+int r433b_fetch(r433b_ctx *ctx, r433b_results *out)
+{
+    if (!ctx || !out) return R433B_EINVAL;
+    if (!ctx->processed) return fail(ctx, R433B_ESTATE, "r433b_fetch before r433b_process");
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t const st = 0;
+    uint32_t const n_devs = (uint32_t)ctx->devs.size();
+    size_t pk_bytes = (size_t)ctx->n_pkgs * sizeof(r433b_package);
+    size_t pool_bytes = (size_t)ctx->pool_used * sizeof(int);
+    size_t pair_bytes = (size_t)ctx->n_pkgs * n_devs * sizeof(r433b_pair);
+    CU(cudaEventRecord(ctx->ev[4], st));
+    if (int r = host_reserve(ctx, ctx->h_pkgs, pk_bytes + 16)) return r;
+    if (int r = host_reserve(ctx, ctx->h_ppool, pool_bytes + 16)) return r;
+    if (int r = host_reserve(ctx, ctx->h_gpool, pool_bytes + 16)) return r;
+    if (int r = host_reserve(ctx, ctx->h_pairs, pair_bytes + 16)) return r;
+    if (int r = host_reserve(ctx, ctx->h_events, ctx->event_bytes + 16)) return r;
+    if (pk_bytes) CU(cudaMemcpyAsync(ctx->h_pkgs.p, ctx->d_pkgs.p, pk_bytes, cudaMemcpyDeviceToHost, st));
+    if (pool_bytes) {
+        CU(cudaMemcpyAsync(ctx->h_ppool.p, ctx->d_ppool.p, pool_bytes, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(ctx->h_gpool.p, ctx->d_gpool.p, pool_bytes, cudaMemcpyDeviceToHost, st));
+    }
+    if (pair_bytes && ctx->d_pairs.p) CU(cudaMemcpyAsync(ctx->h_pairs.p, ctx->d_pairs.p, pair_bytes, cudaMemcpyDeviceToHost, st));
+    if (ctx->event_bytes) CU(cudaMemcpyAsync(ctx->h_events.p, ctx->d_arena.p, ctx->event_bytes, cudaMemcpyDeviceToHost, st));
+    CU(cudaEventRecord(ctx->ev[5], st));
+    CU(cudaEventSynchronize(ctx->ev[5]));
+    cudaEventElapsedTime(&ctx->timing.d2h_ms, ctx->ev[4], ctx->ev[5]);
+    // the device wrote packages in completion order; the reference's order is per stream
+    r433b_package *pk = (r433b_package *)ctx->h_pkgs.p;
+    if (!ctx->fetched)
+        std::sort(pk, pk + ctx->n_pkgs, [](r433b_package const &a, r433b_package const &b) {
+            return a.stream != b.stream ? a.stream < b.stream : a.seq < b.seq;
+        });
+    ctx->fetched = true;
+    out->n_packages = ctx->n_pkgs;
+    out->n_devices = n_devs;
+    out->packages = pk;
+    out->pulse_pool = (int32_t const *)ctx->h_ppool.p;
+    out->gap_pool = (int32_t const *)ctx->h_gpool.p;
+    out->pairs = (r433b_pair const *)ctx->h_pairs.p;
+    out->events = (uint8_t const *)ctx->h_events.p;
+    out->event_bytes = ctx->event_bytes;
+    out->n_events = ctx->n_events;
+    out->n_samples = ctx->n_samples;
+    return R433B_OK;
+}
+
+int r433b_copy_stage(r433b_ctx *ctx, uint32_t stream, int16_t *am, int16_t *fm, uint64_t max_samples)
+{
+    if (!ctx || !am || !fm) return R433B_EINVAL;
+    if (!ctx->processed || !ctx->batch.want_stages) return fail(ctx, R433B_ESTATE, "no stage arrays kept (batch.want_stages)");
+    if (stream >= ctx->batch.n_streams) return fail(ctx, R433B_EINVAL, "stream out of range");
+    CU(cudaSetDevice(ctx->device));
+    uint64_t SS = ctx->batch.sample_format;
+    uint64_t first = ctx->offsets[stream] / SS;
+    uint64_t n = (ctx->offsets[stream + 1] - ctx->offsets[stream]) / SS;
+    if (n > max_samples) n = max_samples;
+    if (n) {
+        CU(cudaMemcpy(am, (int16_t const *)ctx->d_am.p + first, n * sizeof(int16_t), cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy(fm, (int16_t const *)ctx->d_fm.p + first, n * sizeof(int16_t), cudaMemcpyDeviceToHost));
+    }
+    return (int)std::min<uint64_t>(n, 0x7fffffff);
+}
+
+// ------------------------------------------------------------------ host-side replay ------
+
+int r433b_event_to_bitbuffer(uint8_t const *ev, uint32_t pair_bytes, uint32_t index, struct bitbuffer *out,
+        uint32_t *consumed)
+{
+    return event_to_bitbuffer(ev, pair_bytes, index, out, consumed);
+}
+
+float r433b_package_file_pos(r433b_ctx const *ctx, r433b_results const *res, uint32_t package)
+{
+    if (!ctx || !res || package >= res->n_packages) return 0.0f;
+    r433b_package const &k = res->packages[package];
+    uint64_t SS = ctx->batch.sample_format;
+    uint64_t bytes = ctx->offsets[k.stream + 1] - ctx->offsets[k.stream];
+    uint32_t bb = ctx->batch.block_bytes;
+    uint64_t n_blocks = (bytes + bb - 1) / bb;
+    if (n_blocks == 0) return 0.0f;
+    // src/rtl_433.c:1839: value set before the block that returned the package was pushed;
+    // the flush keeps the last block's value
+    uint64_t blk = (uint64_t)k.block < n_blocks ? (uint64_t)k.block : n_blocks - 1;
+    unsigned long n_read = (unsigned long)std::min<uint64_t>(bb, bytes - blk * bb);
+    float pos = ((float)(int)blk * bb + n_read) / ctx->batch.samp_rate / (int)SS;
+    return pos;
+}
+
+int r433b_package_to_pulse_data(r433b_ctx const *ctx, r433b_results const *res, uint32_t package, struct pulse_data *pd)
+{
+    if (!ctx || !res || !pd || package >= res->n_packages) return R433B_EINVAL;
+    r433b_package const &k = res->packages[package];
+    memset(pd, 0, sizeof(*pd));
+    pd->offset = k.offset;
+    pd->sample_rate = ctx->batch.samp_rate;
+    pd->start_ago = k.start_ago;
+    pd->end_ago = k.end_ago;
+    pd->num_pulses = k.num_pulses;
+    memcpy(pd->pulse, res->pulse_pool + k.pulse_off, k.pulse_count * sizeof(int));
+    memcpy(pd->gap, res->gap_pool + k.pulse_off, k.pulse_count * sizeof(int));
+    pd->ook_low_estimate = k.ook_low_estimate;
+    pd->ook_high_estimate = k.ook_high_estimate;
+    pd->fsk_f1_est = k.fsk_f1_est;
+    pd->fsk_f2_est = k.fsk_f2_est;
+    // calc_rssi_snr(), src/r_flow.c:35-64 (float32, log10f)
+    float hi = pd->ook_high_estimate > 0 ? pd->ook_high_estimate : 1;
+    float lo = pd->ook_low_estimate > 0 ? pd->ook_low_estimate : 1;
+    int const max_high = ctx->lv.max_high;
+    float top = hi < max_high ? hi : max_high;
+    float asnr = top / lo;
+    uint32_t rate = ctx->batch.samp_rate, center = ctx->batch.center_frequency;
+    float off1 = (float)pd->fsk_f1_est / INT16_MAX * rate / 2.0f;
+    float off2 = (float)pd->fsk_f2_est / INT16_MAX * rate / 2.0f;
+    pd->freq1_hz = off1 + center;
+    pd->freq2_hz = off2 + center;
+    pd->centerfreq_hz = center;
+    pd->depth_bits = ctx->batch.sample_format * 4;
+    if (ctx->batch.sample_format == 2 && !ctx->use_mag) {
+        pd->range_db = 42.1442f;
+        pd->rssi_db = 10.0f * log10f(hi) - 42.1442f;
+        pd->noise_db = 10.0f * log10f(lo) - 42.1442f;
+        pd->snr_db = 10.0f * log10f(asnr);
+    } else {
+        pd->range_db = 84.2884f;
+        pd->rssi_db = 20.0f * log10f(hi) - 84.2884f;
+        pd->noise_db = 20.0f * log10f(lo) - 84.2884f;
+        pd->snr_db = 20.0f * log10f(asnr);
+    }
+    return R433B_OK;
+}
+
+} // extern "C"
+
+namespace {
+
+template <class PerEvent>
+int replay_stream(r433b_ctx *ctx, r433b_results const *res, uint32_t stream, PerEvent &&per_event)
+{
+    if (!ctx || !res) return R433B_EINVAL;
+    if (!ctx->fetched) return fail(ctx, R433B_ESTATE, "dispatch before fetch");
+    uint32_t const n_devs = res->n_devices;
+    // packages are sorted by (stream, seq)
+    r433b_package const *begin = std::lower_bound(res->packages, res->packages + res->n_packages, stream,
+            [](r433b_package const &k, uint32_t s) { return k.stream < s; });
+    static thread_local struct pulse_data pd;
+    static thread_local struct bitbuffer bits;
+    for (r433b_package const *k = begin; k != res->packages + res->n_packages && k->stream == stream; ++k) {
+        uint32_t pi = (uint32_t)(k - res->packages);
+        r433b_package_to_pulse_data(ctx, res, pi, &pd);
+        // run_ook_demods()/run_fsk_demods(), src/r_api.c:438-550
+        int p_events = 0;
+        unsigned next = 0;
+        for (unsigned prio = 0; !p_events && prio < 0xffffffffu; prio = next) {
+            next = 0xffffffffu;
+            for (uint32_t dv = 0; dv < n_devs; ++dv) {
+                unsigned dp = ctx->devs[dv].priority;
+                if (dp > prio && dp < next) next = dp;
+                if (dp != prio) continue;
+                if (!device_takes((int)ctx->devs[dv].modulation, k->type)) continue;
+                r433b_pair const &pr = res->pairs[(size_t)k->first_pair + dv];
+                uint32_t at = 0;
+                for (uint32_t e = 0; e < pr.events; ++e) {
+                    uint32_t used = 0;
+                    int rc = r433b_event_to_bitbuffer(res->events + pr.offset + at, pr.bytes - at, 0, &bits, &used);
+                    if (rc) return fail(ctx, rc, "corrupt event stream");
+                    at += used;
+                    int ret = per_event(pi, dv, &pd, &bits);
+                    if (ret < -4) return fail(ctx, R433B_EINVAL, "decoder returned an invalid code (< -4)");
+                    if (ret > 0) p_events += ret;
+                }
+            }
+        }
+    }
+    return R433B_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+int r433b_dispatch(r433b_ctx *ctx, r433b_results const *res, uint32_t stream, r433b_event_fn fn, void *user)
+{
+    if (!fn) return R433B_EINVAL;
+    return replay_stream(ctx, res, stream, [&](uint32_t pk, uint32_t dv, struct pulse_data *pd, struct bitbuffer *bits) {
+        return fn(user, pk, dv, pd, bits);
+    });
+}
+
+int r433b_dispatch_r_devices(r433b_ctx *ctx, r433b_results const *res, uint32_t stream, struct r_device *const *devs,
+        uint32_t n)
+{
+    if (!devs || !res || n != res->n_devices) return R433B_EINVAL;
+    return replay_stream(ctx, res, stream, [&](uint32_t, uint32_t dv, struct pulse_data *, struct bitbuffer *bits) {
+        // account_event(), src/pulse_slicer.c:26-66
+        struct r_device *d = devs[dv];
+        int ret = 0;
+        if (d->decode_fn) ret = d->decode_fn(d, bits);
+        d->decode_events += 1;
+        if (ret > 0) {
+            d->decode_ok += 1;
+            d->decode_messages += ret;
+        } else if (ret >= -4) {
+            d->decode_fails[-ret] += 1;
+            ret = 0;
+        }
+        return ret;
+    });
+}
+
+} // extern "C"

@@ -1,0 +1,505 @@
+// r433b_kernels.cuh -- sm_100a kernels of the IQ -> package -> event path.
+//
+//   k_detect<SS> : one WARP per capture stream, walking it tile by tile with all carried state
+//                  in registers.  Per tile: 128-bit loads of the lane's contiguous IQ chunk,
+//                  envelope / phase-discriminator maps in parallel on all lanes, the two
+//                  integer IIR low-passes evaluated EXACTLY in parallel (bracket rounds, below),
+//                  AM/FM tile staged in shared memory, then the package detector state machine
+//                  over the tile (warp-uniform, with warp-ballot scans for the threshold-constant
+//                  states).  IQ is read once; intermediates never touch HBM.
+//   k_slice      : one thread per (package, device): slicer run twice (count, then store) with a
+//                  warp-aggregated arena allocation in between.
+//
+// Exact parallel IIR.  y' = (a*y + c[n]) >> 14 is monotone in y and contracts by a/2^14 per
+// sample, but the floor makes it non-associative.  Each lane owns C consecutive samples and
+// keeps a bracket [lo, hi] for the filter state at the start of its chunk (lane 0: the exact
+// carried state; others: the full int16 range).  One "round" pushes both ends through the
+// PREVIOUS lane's chunk; monotonicity keeps the true state inside, contraction shrinks the
+// bracket by a^C per round, and after every round at least one more lane is exact, so the loop
+// terminates in <= 31 rounds (constant input, where lo/hi sit on different fixed points of the
+// floor map) and typically in 3.  Lanes then run their chunk once from the exact state.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/r433b.h"
+#include "r433b_core.cuh"
+#include "r433b_slice.cuh"
+
+namespace r433b {
+
+constexpr int kTrainInts = 4 * kMaxPulses; // per-stream scratch: ook pulse/gap, fsk pulse/gap
+constexpr int kDetectWarps = 4;            // warps (streams) per CTA
+constexpr int kPadHalf = 8;                // shared-memory chunk padding, in int16 units
+
+struct DetectParams {
+    uint8_t const *data;
+    unsigned long long const *offsets; // bytes, n_streams + 1
+    unsigned n_streams;
+    int use_mag, enable_fm, fpdm;
+    unsigned rate, block_samples;
+    Levels lv;
+    int lpf_a1, lpf_b0, fm_a1, fm_b0;
+    int wrap_free;
+    int *train_scratch;
+    r433b_package *pkgs;
+    unsigned pkg_cap;
+    int *pulse_pool, *gap_pool;
+    unsigned pool_cap;
+    unsigned *counters; // [0] packages, [1] pool entries, [2] overflow flag
+    int16_t *am_out, *fm_out; // optional stage dump, indexed by offsets[s]/SS + n
+};
+
+struct WarpCtx {
+    int lane;
+    int nlanes;
+    __device__ __forceinline__ void sync() { __syncwarp(); }
+};
+
+template <int C>
+__device__ __forceinline__ int tile_index(int n)
+{
+    return n + (n / C) * kPadHalf;
+}
+
+// ------------------------------------------------------------------------ k_detect ------
+
+template <int SS>
+struct TileCfg {
+    static constexpr int C = SS == 2 ? 32 : 16; // samples per lane per tile (64 bytes of IQ)
+    static constexpr int T = 32 * C;
+    static constexpr int kTileHalf = 32 * (C + kPadHalf); // int16 slots per stage array
+};
+
+template <int SS>
+__global__ void __launch_bounds__(kDetectWarps * 32) k_detect(DetectParams p)
+{
+    using Cfg = TileCfg<SS>;
+    constexpr int C = Cfg::C;
+    constexpr int T = Cfg::T;
+    extern __shared__ __align__(16) int16_t smem[];
+
+    int const warp = threadIdx.x >> 5;
+    int const lane = threadIdx.x & 31;
+    unsigned const s = blockIdx.x * kDetectWarps + warp;
+    if (s >= p.n_streams) return;
+
+    int16_t *am_s = smem + warp * 2 * Cfg::kTileHalf;
+    int16_t *fm_s = am_s + Cfg::kTileHalf;
+
+    unsigned long long const byte0 = p.offsets[s];
+    unsigned long long const N = (p.offsets[s + 1] - byte0) / SS;
+    uint8_t const *src = p.data + byte0;
+    unsigned long long const sample0 = byte0 / SS;
+
+    Trains tr;
+    tr.ook_pulse = p.train_scratch + (size_t)s * kTrainInts;
+    tr.ook_gap = tr.ook_pulse + kMaxPulses;
+    tr.fsk_pulse = tr.ook_gap + kMaxPulses;
+    tr.fsk_gap = tr.fsk_pulse + kMaxPulses;
+
+    WarpCtx cx;
+    cx.lane = lane;
+    cx.nlanes = 32;
+
+    DetState d;
+    det_reset(d);
+    d.ook_hw = d.fsk_hw = kMaxPulses; // scratch is not assumed to be zero: first package clears it
+    unsigned seq = 0;
+    int const per_ms = (int)(p.rate / 1000);
+    unsigned long long const n_blocks = (N + p.block_samples - 1) / p.block_samples;
+
+    // carried filter / demod state (reset_sdr_flow(): all zero)
+    int y_am = 0, y_fm = 0;
+    int x_prev = 0;          // raw envelope of the previous sample
+    int xf_prev = 0;         // previous discriminator output
+    int pr_prev = 0, pi_prev = 0; // previous IQ sample (offset removed)
+
+    auto emit = [&](int type, unsigned long long pos, bool flush) {
+        PackageHeader h = package_header(d, type);
+        unsigned cnt = h.num_pulses + 1 < (unsigned)kMaxPulses ? h.num_pulses + 1 : (unsigned)kMaxPulses;
+        unsigned idx = 0, off = 0;
+        if (lane == 0) {
+            idx = atomicAdd(&p.counters[0], 1u);
+            off = atomicAdd(&p.counters[1], cnt);
+        }
+        idx = __shfl_sync(0xffffffffu, idx, 0);
+        off = __shfl_sync(0xffffffffu, off, 0);
+        bool fits = idx < p.pkg_cap && (unsigned long long)off + cnt <= p.pool_cap;
+        if (!fits) {
+            if (lane == 0) atomicOr(&p.counters[2], 1u);
+        } else {
+            __syncwarp();
+            int const *sp = type == 1 ? tr.ook_pulse : tr.fsk_pulse;
+            int const *sg = type == 1 ? tr.ook_gap : tr.fsk_gap;
+            for (unsigned i = lane; i < cnt; i += 32) {
+                p.pulse_pool[off + i] = sp[i];
+                p.gap_pool[off + i] = sg[i];
+            }
+            if (lane == 0) {
+                unsigned long long blk = flush ? n_blocks : pos / p.block_samples;
+                unsigned long long bstart = blk * p.block_samples;
+                unsigned long long blen = flush ? 0 : (N - bstart < p.block_samples ? N - bstart : p.block_samples);
+                r433b_package k;
+                k.stream = s;
+                k.seq = seq;
+                k.type = type;
+                k.block = (int)blk;
+                k.offset = h.offset;
+                k.end_pos = pos;
+                k.start_ago = flush ? (unsigned)(N - h.start_abs) : (unsigned)(bstart + blen - h.start_abs);
+                k.end_ago = flush ? 0u : (unsigned)(blen - (pos - bstart));
+                k.num_pulses = h.num_pulses;
+                k.pulse_off = off;
+                k.pulse_count = cnt;
+                k.ook_low_estimate = h.low;
+                k.ook_high_estimate = h.high;
+                k.fsk_f1_est = h.f1;
+                k.fsk_f2_est = h.f2;
+                k.first_pair = 0;
+                p.pkgs[idx] = k;
+            }
+        }
+        seq++;
+    };
+
+    for (unsigned long long t0 = 0; t0 < N; t0 += T) {
+        unsigned long long const remain = N - t0;
+        int const nv_tile = remain < (unsigned long long)T ? (int)remain : T;
+        int nv = nv_tile - lane * C; // valid samples in this lane's chunk
+        nv = nv < 0 ? 0 : (nv > C ? C : nv);
+
+        // ---- load the lane's 64 bytes of IQ ------------------------------------------
+        uint32_t raw[16];
+        {
+            uint8_t const *g = src + (t0 + (unsigned long long)lane * C) * SS;
+            if (nv == C) {
+                uint4 const *g4 = reinterpret_cast<uint4 const *>(g);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    uint4 v = __ldg(g4 + q);
+                    raw[4 * q + 0] = v.x;
+                    raw[4 * q + 1] = v.y;
+                    raw[4 * q + 2] = v.z;
+                    raw[4 * q + 3] = v.w;
+                }
+            } else {
+#pragma unroll
+                for (int q = 0; q < 16; ++q) {
+                    uint32_t w = 0;
+                    for (int b = 0; b < 4; ++b) {
+                        int byte = q * 4 + b;
+                        if (byte < nv * SS) w |= (uint32_t)g[byte] << (8 * b);
+                    }
+                    raw[q] = w;
+                }
+            }
+        }
+
+        // ---- sample maps: envelope x[k] and discriminator xf[k] ------------------------
+        // previous IQ sample for the first sample of the chunk comes from the lane to the left
+        int xs[C];  // envelope (uint16 range)
+        int xfv[C]; // discriminator output (int16 for cu8, int32 for cs16); raw envelope if FM is off
+        {
+            int last_i, last_q;
+            if (SS == 2) {
+                last_i = (int)((raw[15] >> 16) & 0xff) - 128;
+                last_q = (int)((raw[15] >> 24) & 0xff) - 128;
+            } else {
+                last_i = (int)(int16_t)(raw[15] & 0xffff);
+                last_q = (int)(int16_t)(raw[15] >> 16);
+            }
+            int pi_ = __shfl_up_sync(0xffffffffu, last_i, 1);
+            int pq_ = __shfl_up_sync(0xffffffffu, last_q, 1);
+            if (lane == 0) {
+                pi_ = pr_prev;
+                pq_ = pi_prev;
+            }
+#pragma unroll
+            for (int k = 0; k < C; ++k) {
+                int ci, cq, ri, rq;
+                if (SS == 2) {
+                    uint32_t w = raw[k >> 1];
+                    ri = (int)((w >> ((k & 1) * 16)) & 0xff);
+                    rq = (int)((w >> ((k & 1) * 16 + 8)) & 0xff);
+                    ci = ri - 128;
+                    cq = rq - 128;
+                    xs[k] = p.use_mag ? mag_cu8(ri, rq) : env_cu8(ri, rq);
+                } else {
+                    uint32_t w = raw[k];
+                    ci = (int)(int16_t)(w & 0xffff);
+                    cq = (int)(int16_t)(w >> 16);
+                    xs[k] = mag_cs16(ci, cq);
+                }
+                if (p.enable_fm) {
+                    if (SS == 2) {
+                        int re = ci * pi_ + cq * pq_;
+                        int im = cq * pi_ - ci * pq_;
+                        xfv[k] = atan16(im, re);
+                    } else {
+                        long long re = (long long)ci * pi_ + (long long)cq * pq_;
+                        long long im = (long long)cq * pi_ - (long long)ci * pq_;
+                        xfv[k] = atan32((int)(unsigned)(unsigned long long)im, (int)(unsigned)(unsigned long long)re);
+                    }
+                } else {
+                    xfv[k] = (int)(int16_t)xs[k];
+                }
+                pi_ = ci;
+                pq_ = cq;
+            }
+            // carry the last VALID sample of the tile to the next tile (lane 31 when full)
+            int src_lane = (nv_tile - 1) / C;
+            int kk = (nv_tile - 1) % C;
+            int li = 0, lq = 0;
+            {
+                int ci = 0, cq = 0;
+#pragma unroll
+                for (int k = 0; k < C; ++k) {
+                    if (k == kk) {
+                        if (SS == 2) {
+                            uint32_t w = raw[k >> 1];
+                            ci = (int)((w >> ((k & 1) * 16)) & 0xff) - 128;
+                            cq = (int)((w >> ((k & 1) * 16 + 8)) & 0xff) - 128;
+                        } else {
+                            ci = (int)(int16_t)(raw[k] & 0xffff);
+                            cq = (int)(int16_t)(raw[k] >> 16);
+                        }
+                    }
+                }
+                li = __shfl_sync(0xffffffffu, ci, src_lane);
+                lq = __shfl_sync(0xffffffffu, cq, src_lane);
+            }
+            pr_prev = li;
+            pi_prev = lq;
+        }
+
+        // ---- the two IIR low-passes, exact and lane-parallel -----------------------------
+        // inputs to the first sample of the chunk: previous envelope / discriminator values
+        int xl = __shfl_up_sync(0xffffffffu, xs[C - 1], 1);
+        int fl = __shfl_up_sync(0xffffffffu, xfv[C - 1], 1);
+        if (lane == 0) {
+            // the reference keeps x[-1] as int16 across block calls (src/baseband.c:167)
+            xl = (t0 % p.block_samples == 0) ? (int)(int16_t)x_prev : x_prev;
+            fl = xf_prev;
+        }
+        bool const fm_on = p.enable_fm != 0;
+        int const a1 = p.lpf_a1, b0 = p.lpf_b0;
+        long long const fa1 = p.fm_a1, fb0 = p.fm_b0;
+
+        auto run_chunk = [&](int &ya, int &yf) {
+            int xp = xl, fp = fl;
+#pragma unroll
+            for (int k = 0; k < C; ++k) {
+                if (k < nv) {
+                    ya = iir16(ya, a1, b0, xs[k] + xp);
+                    xp = xs[k];
+                    if (fm_on) {
+                        if (SS == 2)
+                            yf = iir16(yf, (int)fa1, (int)fb0, xfv[k] + fp);
+                        else
+                            yf = iir32(yf, fa1, fb0, (long long)xfv[k] + fp);
+                        fp = xfv[k];
+                    }
+                }
+            }
+        };
+
+        int lo_a, hi_a, lo_f, hi_f;
+        if (lane == 0) {
+            lo_a = hi_a = y_am;
+            lo_f = hi_f = y_fm;
+        } else {
+            lo_a = -32768;
+            hi_a = 32767;
+            lo_f = SS == 2 ? -32768 : (int)0x80000000;
+            hi_f = SS == 2 ? 32767 : 0x7fffffff;
+        }
+        for (int round = 0; round < 31; ++round) {
+            bool mine = (lo_a == hi_a) && (!fm_on || lo_f == hi_f);
+            // lanes 0..round are exact by induction even if the filter could wrap
+            bool trust = p.wrap_free ? mine : (lane <= round);
+            if (__all_sync(0xffffffffu, trust)) break;
+            int ea_lo = lo_a, ea_hi = hi_a, ef_lo = lo_f, ef_hi = hi_f;
+            run_chunk(ea_lo, ef_lo);
+            run_chunk(ea_hi, ef_hi);
+            int na_lo = __shfl_up_sync(0xffffffffu, ea_lo, 1);
+            int na_hi = __shfl_up_sync(0xffffffffu, ea_hi, 1);
+            int nf_lo = __shfl_up_sync(0xffffffffu, ef_lo, 1);
+            int nf_hi = __shfl_up_sync(0xffffffffu, ef_hi, 1);
+            if (lane != 0) {
+                lo_a = na_lo;
+                hi_a = na_hi;
+                lo_f = nf_lo;
+                hi_f = nf_hi;
+            }
+        }
+
+        // final pass from the exact state, writing the stage tile
+        {
+            int ya = lo_a, yf = lo_f;
+            int xp = xl, fp = fl;
+            int16_t *am_w = am_s + lane * (C + kPadHalf);
+            int16_t *fm_w = fm_s + lane * (C + kPadHalf);
+            uint32_t pack_a[C / 2], pack_f[C / 2];
+#pragma unroll
+            for (int k = 0; k < C; ++k) {
+                int fo;
+                if (k < nv) {
+                    ya = iir16(ya, a1, b0, xs[k] + xp);
+                    xp = xs[k];
+                    if (fm_on) {
+                        if (SS == 2) {
+                            yf = iir16(yf, (int)fa1, (int)fb0, xfv[k] + fp);
+                            fo = yf;
+                        } else {
+                            yf = iir32(yf, fa1, fb0, (long long)xfv[k] + fp);
+                            fo = yf >> 16;
+                        }
+                        fp = xfv[k];
+                    } else {
+                        fo = xfv[k];
+                    }
+                } else {
+                    fo = 0;
+                }
+                uint32_t av = (uint32_t)(uint16_t)(int16_t)ya;
+                uint32_t fv = (uint32_t)(uint16_t)(int16_t)fo;
+                if (k & 1) {
+                    pack_a[k >> 1] |= av << 16;
+                    pack_f[k >> 1] |= fv << 16;
+                } else {
+                    pack_a[k >> 1] = av;
+                    pack_f[k >> 1] = fv;
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < C / 8; ++q) {
+                reinterpret_cast<uint4 *>(am_w)[q] = make_uint4(pack_a[4 * q], pack_a[4 * q + 1], pack_a[4 * q + 2], pack_a[4 * q + 3]);
+                reinterpret_cast<uint4 *>(fm_w)[q] = make_uint4(pack_f[4 * q], pack_f[4 * q + 1], pack_f[4 * q + 2], pack_f[4 * q + 3]);
+            }
+            if (p.am_out) {
+                unsigned long long base = sample0 + t0 + (unsigned long long)lane * C;
+                for (int k = 0; k < nv; ++k) {
+                    p.am_out[base + k] = (int16_t)(pack_a[k >> 1] >> ((k & 1) * 16));
+                    p.fm_out[base + k] = (int16_t)(pack_f[k >> 1] >> ((k & 1) * 16));
+                }
+            }
+            // carries for the next tile: the state after the last valid sample (identity steps
+            // in lanes past the end make lane 31 hold it)
+            int last_lane = (nv_tile - 1) / C;
+            y_am = __shfl_sync(0xffffffffu, ya, last_lane);
+            y_fm = __shfl_sync(0xffffffffu, yf, last_lane);
+            x_prev = __shfl_sync(0xffffffffu, xp, last_lane);
+            xf_prev = __shfl_sync(0xffffffffu, fp, last_lane);
+        }
+        __syncwarp();
+
+        // ---- package detector over the tile (warp-uniform) -------------------------------
+        if (t0 % p.block_samples == 0) det_call_boundary(d, p.lv);
+        for (int n = 0; n < nv_tile;) {
+            int idx = tile_index<C>(n);
+            int a = am_s[idx];
+            int f = fm_s[idx];
+            int ev = det_step(d, p.lv, tr, a, f, t0 + n, per_ms, p.fpdm, cx);
+            if (ev) {
+                emit(ev, t0 + n, false);
+                det_call_boundary(d, p.lv);
+                continue; // the same sample is examined again, now in IDLE
+            }
+            ++n;
+        }
+        __syncwarp();
+    }
+
+    // flush_sdr_flow(): len == 0 call(s) at the end of the file
+    for (;;) {
+        int ev = det_flush(d, tr, p.fpdm);
+        if (!ev) break;
+        emit(ev, N, true);
+    }
+}
+
+// ------------------------------------------------------------------------- k_slice -------
+
+struct SliceParams {
+    r433b_package *pkgs;
+    unsigned n_pkgs;
+    int const *pulse_pool, *gap_pool;
+    SlicerParams const *dev;  // per device, already scaled to the batch sample rate
+    unsigned n_devs;
+    unsigned const *ook_list, *fsk_list; // device indices taking OOK / FSK packages, grouped by modulation
+    unsigned n_ook, n_fsk;
+    r433b_pair *pairs;        // n_pkgs * n_devs, pre-zeroed
+    uint8_t *arena;
+    unsigned long long arena_cap;
+    unsigned long long *cursor; // [0] bytes reserved, [1] events, [2] overflow
+};
+
+constexpr int kSliceThreads = 128;
+
+__global__ void __launch_bounds__(kSliceThreads) k_slice(SliceParams p)
+{
+    unsigned const pk = blockIdx.x;
+    if (pk >= p.n_pkgs) return;
+    r433b_package const k = p.pkgs[pk];
+    unsigned const n_list = k.type == 1 ? p.n_ook : p.n_fsk;
+    unsigned const *list = k.type == 1 ? p.ook_list : p.fsk_list;
+    if (threadIdx.x == 0) p.pkgs[pk].first_pair = pk * p.n_devs;
+
+    PulseView pv;
+    pv.pulse = p.pulse_pool + k.pulse_off;
+    pv.gap = p.gap_pool + k.pulse_off;
+    pv.n = k.num_pulses;
+
+    for (unsigned base = 0; base < n_list; base += blockDim.x) {
+        unsigned slot = base + threadIdx.x;
+        bool active = slot < n_list;
+        unsigned dev = active ? list[slot] : 0;
+        unsigned bytes = 0, nev = 0;
+        SlicerParams sp;
+        if (active) {
+            sp = p.dev[dev];
+            EventWriter<false> cw;
+            cw.init(nullptr);
+            slice_dispatch(pv, sp, cw);
+            bytes = cw.committed;
+            nev = cw.events;
+        }
+        // warp-aggregated reservation in the event arena
+        unsigned incl = bytes;
+        unsigned lane = threadIdx.x & 31;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            unsigned v = __shfl_up_sync(0xffffffffu, incl, o);
+            if ((int)lane >= o) incl += v;
+        }
+        unsigned total = __shfl_sync(0xffffffffu, incl, 31);
+        unsigned evs = nev;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) evs += __shfl_xor_sync(0xffffffffu, evs, o);
+        unsigned long long wbase = 0;
+        if (lane == 0 && total) {
+            wbase = atomicAdd(p.cursor, (unsigned long long)total);
+            atomicAdd(p.cursor + 1, (unsigned long long)evs);
+        }
+        wbase = __shfl_sync(0xffffffffu, wbase, 0);
+        unsigned long long off = wbase + incl - bytes;
+        if (active) {
+            bool fits = off + bytes <= p.arena_cap;
+            if (bytes && fits) {
+                EventWriter<true> sw;
+                sw.init(p.arena + off, bytes);
+                slice_dispatch(pv, sp, sw);
+            } else if (bytes) {
+                atomicOr(p.cursor + 2, 1ull);
+            }
+            r433b_pair pr;
+            pr.offset = off;
+            pr.bytes = bytes;
+            pr.events = nev;
+            p.pairs[(size_t)pk * p.n_devs + dev] = pr;
+        }
+    }
+}
+
+} // namespace r433b

@@ -1,0 +1,282 @@
+"""ctypes binding of the C ABI in include/r433b.h (rtl_433_b200/csrc/libr433b.so).
+
+Python is plumbing only: every sample is processed by the CUDA kernels inside the shared
+library.  If the library is missing or no CUDA device is usable this module raises; there is
+no CPU path.
+"""
+import ctypes as C
+import json
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB_PATH = os.path.join(CSRC, "libr433b.so")
+
+FMT_CU8, FMT_CS16 = 2, 4
+FPDM_CLASSIC, FPDM_MINMAX, FPDM_AUTO = 0, 1, 2
+PACKAGE_OOK, PACKAGE_FSK = 1, 2
+
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false",
+              "-shared", "-Xcompiler", "-fPIC,-ffp-contract=off"]
+
+EXPORTS = ["r433b_create", "r433b_destroy", "r433b_last_error", "r433b_set_levels", "r433b_set_fm_low_pass",
+           "r433b_set_devices", "r433b_set_r_devices", "r433b_process", "r433b_fetch", "r433b_get_timing",
+           "r433b_get_counts", "r433b_copy_stage", "r433b_event_to_bitbuffer", "r433b_package_to_pulse_data",
+           "r433b_package_file_pos", "r433b_dispatch", "r433b_dispatch_r_devices"]
+
+
+def build(force=False, verbose=False):
+    """nvcc -> csrc/libr433b.so for sm_100a (cross-compiles without a GPU)."""
+    srcs = [os.path.join(CSRC, n) for n in ("r433b_api.cu", "r433b_kernels.cuh", "r433b_core.cuh", "r433b_slice.cuh",
+                                             "r433b_host.hpp")]
+    srcs += [os.path.join(os.path.dirname(HERE), "include", n) for n in ("r433b.h", "r433b_abi.h")]
+    if not force and os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(s) for s in srcs):
+        return LIB_PATH
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH, os.path.join(CSRC, "r433b_api.cu")]
+    subprocess.check_call(cmd)
+    return LIB_PATH
+
+
+class Device(C.Structure):
+    _fields_ = [("modulation", C.c_uint32), ("short_width", C.c_float), ("long_width", C.c_float),
+                ("reset_limit", C.c_float), ("gap_limit", C.c_float), ("sync_width", C.c_float),
+                ("tolerance", C.c_float), ("priority", C.c_uint32)]
+
+
+class Batch(C.Structure):
+    _fields_ = [("data", C.c_void_p), ("offsets", C.POINTER(C.c_uint64)), ("n_streams", C.c_uint32),
+                ("sample_format", C.c_uint32), ("samp_rate", C.c_uint32), ("center_frequency", C.c_uint32),
+                ("fpdm_mode", C.c_uint32), ("block_bytes", C.c_uint32), ("data_on_device", C.c_int32),
+                ("want_stages", C.c_int32)]
+
+
+class Package(C.Structure):
+    _fields_ = [("stream", C.c_uint32), ("seq", C.c_uint32), ("type", C.c_int32), ("block", C.c_int32),
+                ("offset", C.c_uint64), ("end_pos", C.c_uint64), ("start_ago", C.c_uint32), ("end_ago", C.c_uint32),
+                ("num_pulses", C.c_uint32), ("pulse_off", C.c_uint32), ("pulse_count", C.c_uint32),
+                ("ook_low_estimate", C.c_int32), ("ook_high_estimate", C.c_int32), ("fsk_f1_est", C.c_int32),
+                ("fsk_f2_est", C.c_int32), ("first_pair", C.c_uint32)]
+
+
+PACKAGE_DTYPE = np.dtype([("stream", "<u4"), ("seq", "<u4"), ("type", "<i4"), ("block", "<i4"), ("offset", "<u8"),
+                          ("end_pos", "<u8"), ("start_ago", "<u4"), ("end_ago", "<u4"), ("num_pulses", "<u4"),
+                          ("pulse_off", "<u4"), ("pulse_count", "<u4"), ("ook_low_estimate", "<i4"),
+                          ("ook_high_estimate", "<i4"), ("fsk_f1_est", "<i4"), ("fsk_f2_est", "<i4"),
+                          ("first_pair", "<u4")])
+assert PACKAGE_DTYPE.itemsize == C.sizeof(Package) == 72
+
+PAIR_DTYPE = np.dtype([("offset", "<u8"), ("bytes", "<u4"), ("events", "<u4")])
+
+
+class Results(C.Structure):
+    _fields_ = [("n_packages", C.c_uint32), ("n_devices", C.c_uint32), ("packages", C.c_void_p),
+                ("pulse_pool", C.c_void_p), ("gap_pool", C.c_void_p), ("pairs", C.c_void_p), ("events", C.c_void_p),
+                ("event_bytes", C.c_uint64), ("n_events", C.c_uint64), ("n_samples", C.c_uint64)]
+
+
+class Timing(C.Structure):
+    _fields_ = [("h2d_ms", C.c_float), ("detect_ms", C.c_float), ("slice_ms", C.c_float), ("d2h_ms", C.c_float),
+                ("total_ms", C.c_float), ("detect_launches", C.c_uint32), ("slice_launches", C.c_uint32)]
+
+
+class PulseData(C.Structure):
+    _fields_ = [("offset", C.c_uint64), ("sample_rate", C.c_uint32), ("depth_bits", C.c_uint), ("start_ago", C.c_uint),
+                ("end_ago", C.c_uint), ("num_pulses", C.c_uint), ("pulse", C.c_int * 1200), ("gap", C.c_int * 1200),
+                ("ook_low_estimate", C.c_int), ("ook_high_estimate", C.c_int), ("fsk_f1_est", C.c_int),
+                ("fsk_f2_est", C.c_int), ("freq1_hz", C.c_float), ("freq2_hz", C.c_float), ("centerfreq_hz", C.c_float),
+                ("range_db", C.c_float), ("rssi_db", C.c_float), ("snr_db", C.c_float), ("noise_db", C.c_float)]
+
+
+assert C.sizeof(PulseData) == 9672
+
+BITBUFFER_DTYPE = np.dtype([("num_rows", "<u2"), ("free_row", "<u2"), ("bits_per_row", "<u2", (50,)),
+                            ("syncs_before_row", "<u2", (50,)), ("bb", "u1", (50, 128))])
+assert BITBUFFER_DTYPE.itemsize == 6604
+
+EVENT_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(PulseData), C.c_void_p)
+
+_lib = None
+
+
+def load():
+    """dlopen the in-tree library; fails loudly if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(nvcc, sm_100a). There is no CPU fallback.")
+    L = C.CDLL(LIB_PATH)
+    L.r433b_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
+    L.r433b_destroy.argtypes = [C.c_void_p]
+    L.r433b_last_error.restype = C.c_char_p
+    L.r433b_last_error.argtypes = [C.c_void_p]
+    L.r433b_set_levels.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_float]
+    L.r433b_set_fm_low_pass.argtypes = [C.c_void_p, C.c_float]
+    L.r433b_set_devices.argtypes = [C.c_void_p, C.POINTER(Device), C.c_uint32]
+    L.r433b_set_r_devices.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
+    L.r433b_process.argtypes = [C.c_void_p, C.POINTER(Batch)]
+    L.r433b_fetch.argtypes = [C.c_void_p, C.POINTER(Results)]
+    L.r433b_get_timing.argtypes = [C.c_void_p, C.POINTER(Timing)]
+    L.r433b_get_counts.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
+    L.r433b_copy_stage.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint64]
+    L.r433b_event_to_bitbuffer.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.POINTER(C.c_uint32)]
+    L.r433b_package_to_pulse_data.argtypes = [C.c_void_p, C.POINTER(Results), C.c_uint32, C.POINTER(PulseData)]
+    L.r433b_package_file_pos.restype = C.c_float
+    L.r433b_package_file_pos.argtypes = [C.c_void_p, C.POINTER(Results), C.c_uint32]
+    L.r433b_dispatch.argtypes = [C.c_void_p, C.POINTER(Results), C.c_uint32, EVENT_FN, C.c_void_p]
+    L.r433b_dispatch_r_devices.argtypes = [C.c_void_p, C.POINTER(Results), C.c_uint32, C.c_void_p, C.c_uint32]
+    _lib = L
+    return L
+
+
+def default_device_table(include_disabled=False):
+    """The reference's r_device table (rtl_433_b200/data/devices_25.12.json)."""
+    with open(os.path.join(HERE, "data", "devices_25.12.json")) as f:
+        devs = json.load(f)["devices"]
+    return [d for d in devs if include_disabled or d["disabled"] == 0]
+
+
+class R433Error(RuntimeError):
+    pass
+
+
+class Context:
+    """One GPU context (include/r433b.h: r433b_ctx)."""
+
+    def __init__(self, cuda_device=0):
+        self.L = load()
+        h = C.c_void_p()
+        rc = self.L.r433b_create(cuda_device, C.byref(h))
+        if rc != 0:
+            raise R433Error(f"r433b_create failed ({rc}): no usable CUDA device; there is no CPU fallback")
+        self.h = h
+        self._keep = None
+        self.n_devices = 0
+
+    def close(self):
+        if self.h:
+            self.L.r433b_destroy(self.h)
+            self.h = None
+
+    def _check(self, rc):
+        if rc < 0:
+            raise R433Error(f"r433b error {rc}: {self.L.r433b_last_error(self.h).decode()}")
+        return rc
+
+    def set_levels(self, use_mag_est=0, level_limit=0.0, min_level=-12.1442, min_snr=9.0):
+        self._check(self.L.r433b_set_levels(self.h, use_mag_est, level_limit, min_level, min_snr))
+
+    def set_fm_low_pass(self, v):
+        self._check(self.L.r433b_set_fm_low_pass(self.h, v))
+
+    def set_devices(self, devs):
+        arr = (Device * len(devs))()
+        for i, d in enumerate(devs):
+            arr[i] = Device(d["modulation"], d["short_width"], d["long_width"], d["reset_limit"], d.get("gap_limit", 0.0),
+                            d.get("sync_width", 0.0), d.get("tolerance", 0.0), d.get("priority", 0))
+        self._check(self.L.r433b_set_devices(self.h, arr, len(devs)))
+        self.n_devices = len(devs)
+
+    def process(self, data, offsets, sample_format, samp_rate=250000, center_frequency=433920000, fpdm_mode=FPDM_AUTO,
+                block_bytes=0, data_on_device=False, want_stages=False):
+        """`data`: host numpy array (any dtype, contiguous) or an int device pointer."""
+        offs = np.ascontiguousarray(offsets, dtype=np.uint64)
+        if isinstance(data, int):
+            ptr = data
+        else:
+            data = np.ascontiguousarray(data)
+            ptr = data.ctypes.data
+        b = Batch(ptr, offs.ctypes.data_as(C.POINTER(C.c_uint64)), len(offs) - 1, sample_format, samp_rate,
+                  center_frequency, fpdm_mode, block_bytes, int(data_on_device), int(want_stages))
+        self._keep = (data, offs)
+        self._check(self.L.r433b_process(self.h, C.byref(b)))
+
+    def counts(self):
+        out = (C.c_uint64 * 4)()
+        self._check(self.L.r433b_get_counts(self.h, out))
+        return {"packages": out[0], "events": out[1], "event_bytes": out[2], "samples": out[3]}
+
+    def timing(self):
+        t = Timing()
+        self._check(self.L.r433b_get_timing(self.h, C.byref(t)))
+        return {k: getattr(t, k) for k, _ in Timing._fields_}
+
+    def fetch(self):
+        """-> dict of numpy views over the context's pinned host buffers."""
+        r = Results()
+        self._check(self.L.r433b_fetch(self.h, C.byref(r)))
+        self._res = r
+
+        def view(ptr, nbytes, dtype):
+            if not nbytes:
+                return np.zeros(0, dtype)
+            return np.frombuffer((C.c_uint8 * nbytes).from_address(ptr), dtype=dtype)
+
+        npk = r.n_packages
+        pk = view(r.packages, npk * 72, PACKAGE_DTYPE)
+        pool_n = int((pk["pulse_off"].astype(np.int64) + pk["pulse_count"]).max()) if npk else 0
+        return {"n_packages": npk, "n_devices": r.n_devices, "packages": pk,
+                "pulse_pool": view(r.pulse_pool, pool_n * 4, np.int32), "gap_pool": view(r.gap_pool, pool_n * 4, np.int32),
+                "pairs": view(r.pairs, npk * r.n_devices * 16, PAIR_DTYPE).reshape(npk, r.n_devices) if npk and r.n_devices else np.zeros((0, 0), PAIR_DTYPE),
+                "events": view(r.events, r.event_bytes, np.uint8), "event_bytes": r.event_bytes, "n_events": r.n_events,
+                "n_samples": r.n_samples}
+
+    def copy_stage(self, stream, n):
+        am = np.zeros(n, np.int16)
+        fm = np.zeros(n, np.int16)
+        got = self._check(self.L.r433b_copy_stage(self.h, stream, am.ctypes.data, fm.ctypes.data, n))
+        return am[:got], fm[:got]
+
+    def pulse_data(self, package_index):
+        pd = PulseData()
+        self._check(self.L.r433b_package_to_pulse_data(self.h, C.byref(self._res), package_index, C.byref(pd)))
+        return pd
+
+    def file_pos(self, package_index):
+        return self.L.r433b_package_file_pos(self.h, C.byref(self._res), package_index)
+
+    def dispatch(self, stream, fn):
+        """fn(package_index, device_index, PulseData, bitbuffer numpy record) -> int"""
+        def tramp(_user, pk, dv, pd, bits):
+            bb = np.frombuffer((C.c_uint8 * 6604).from_address(bits), dtype=BITBUFFER_DTYPE)[0]
+            return int(fn(pk, dv, pd.contents, bb) or 0)
+        cb = EVENT_FN(tramp)
+        self._check(self.L.r433b_dispatch(self.h, C.byref(self._res), stream, cb, None))
+
+    def dispatch_native(self, stream, fn_ptr, user_ptr):
+        """r433b_dispatch() with a native r433b_event_fn (address) and user pointer."""
+        fn = C.cast(fn_ptr, EVENT_FN)
+        self._check(self.L.r433b_dispatch(self.h, C.byref(self._res), stream, fn, user_ptr))
+
+    def packages_of(self, stream):
+        """Package dicts of one stream (integer header, float levels, widths) in order."""
+        r = self._res
+        npk = r.n_packages
+        if not npk:
+            return [], []
+        pk = np.frombuffer((C.c_uint8 * (npk * 72)).from_address(r.packages), dtype=PACKAGE_DTYPE)
+        pool_n = int((pk["pulse_off"].astype(np.int64) + pk["pulse_count"]).max())
+        pp = np.frombuffer((C.c_uint8 * (pool_n * 4)).from_address(r.pulse_pool), dtype=np.int32)
+        gp = np.frombuffer((C.c_uint8 * (pool_n * 4)).from_address(r.gap_pool), dtype=np.int32)
+        out, index = [], []
+        for gi in np.nonzero(pk["stream"] == stream)[0]:
+            k = pk[gi]
+            pd = self.pulse_data(int(gi))
+            out.append({"type": int(k["type"]), "block": int(k["block"]), "offset": int(k["offset"]),
+                        "sample_rate": pd.sample_rate, "depth_bits": pd.depth_bits, "start_ago": int(k["start_ago"]),
+                        "end_ago": int(k["end_ago"]), "num_pulses": int(k["num_pulses"]),
+                        "ook_low_estimate": int(k["ook_low_estimate"]), "ook_high_estimate": int(k["ook_high_estimate"]),
+                        "fsk_f1_est": int(k["fsk_f1_est"]), "fsk_f2_est": int(k["fsk_f2_est"]),
+                        "freq1_hz": pd.freq1_hz, "freq2_hz": pd.freq2_hz, "centerfreq_hz": pd.centerfreq_hz,
+                        "range_db": pd.range_db, "rssi_db": pd.rssi_db, "snr_db": pd.snr_db, "noise_db": pd.noise_db,
+                        "sample_file_pos": self.file_pos(int(gi)), "pulse_count": int(k["pulse_count"]),
+                        "num_events": 0,
+                        "pulse": pp[k["pulse_off"]:k["pulse_off"] + k["pulse_count"]].copy(),
+                        "gap": gp[k["pulse_off"]:k["pulse_off"] + k["pulse_count"]].copy()})
+            index.append(int(gi))
+        return out, index

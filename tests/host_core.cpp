@@ -1,0 +1,331 @@
+// tests/host_core.cpp -- CPU unit-test driver for the __host__ __device__ building blocks of the
+// product (rtl_433_b200/csrc/r433b_core.cuh, r433b_slice.cuh, r433b_host.hpp).
+//
+// TEST CODE ONLY.  It runs the same per-sample functions the sm_100a kernels call, one stream
+// at a time and strictly sequentially, so their logic can be checked against the oracle on a
+// machine without a GPU.  It is never built into, or reachable from, libr433b.so; the warp
+// level orchestration of the kernels (bracket rounds, ballots) is covered by the -m gpu tests.
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "../rtl_433_b200/csrc/r433b_host.hpp"
+
+using namespace r433b;
+
+namespace {
+
+struct HostCtx {
+    int lane = 0;
+    int nlanes = 1;
+    void sync() {}
+};
+
+// same layouts as oracle/ref_harness.c so tests read all three with one reader
+struct hc_package {
+    int32_t type;
+    int32_t block;
+    uint64_t offset;
+    uint32_t sample_rate, depth_bits, start_ago, end_ago, num_pulses;
+    int32_t ook_low_estimate, ook_high_estimate, fsk_f1_est, fsk_f2_est;
+    float freq1_hz, freq2_hz, centerfreq_hz, range_db, rssi_db, snr_db, noise_db;
+    float sample_file_pos;
+    uint32_t pulse_off, pulse_count;
+    uint32_t first_event, num_events;
+};
+
+struct hc_event {
+    uint32_t package;
+    uint32_t dev;
+    int32_t ret;
+    uint32_t bb_idx;
+    uint64_t hash;
+};
+
+uint64_t fnv1a(void const *p, size_t n)
+{
+    uint8_t const *b = (uint8_t const *)p;
+    uint64_t h = 1469598103934665603ull;
+    for (size_t i = 0; i < n; ++i) {
+        h ^= b[i];
+        h *= 1099511628211ull;
+    }
+    return h;
+}
+
+struct Hc {
+    int use_mag = 0;
+    float level_limit = 0.0f, min_level = -12.1442f, min_snr = 9.0f, fm_low_pass = 0.0f;
+    std::vector<r433b_device> devs;
+    int store_bitbuffers = 1, store_stages = 0;
+    std::vector<hc_package> pkgs;
+    std::vector<hc_event> evts;
+    std::vector<bitbuffer> bbs;
+    std::vector<int32_t> ppool, gpool;
+    std::vector<int16_t> am, fm;
+};
+
+void slice_package(Hc &h, int type, uint32_t rate, int const *pulse, int const *gap, unsigned n)
+{
+    PulseView pv{pulse, gap, n};
+    unsigned next = 0;
+    for (unsigned prio = 0; prio < 0xffffffffu; prio = next) {
+        next = 0xffffffffu;
+        for (size_t i = 0; i < h.devs.size(); ++i) {
+            unsigned dp = h.devs[i].priority;
+            if (dp > prio && dp < next) next = dp;
+            if (dp != prio) continue;
+            if (!device_takes((int)h.devs[i].modulation, type)) continue;
+            SlicerParams sp = scale_device(h.devs[i], rate);
+            EventWriter<false> cw;
+            cw.init(nullptr);
+            slice_dispatch(pv, sp, cw);
+            std::vector<uint8_t> buf(cw.committed + 8, 0xAA);
+            EventWriter<true> sw;
+            sw.init(buf.data(), cw.committed);
+            slice_dispatch(pv, sp, sw);
+            for (unsigned g = cw.committed; g < cw.committed + 8; ++g)
+                if (buf[g] != 0xAA) {
+                    fprintf(stderr, "host_core: store pass wrote past its region (dev %zu)\n", i);
+                    abort();
+                }
+            if (sw.committed != cw.committed || sw.events != cw.events) {
+                fprintf(stderr, "host_core: count/store mismatch dev %zu: %u/%u bytes %u/%u events\n", i, cw.committed,
+                        sw.committed, cw.events, sw.events);
+                abort();
+            }
+            uint32_t at = 0;
+            for (unsigned e = 0; e < sw.events; ++e) {
+                bitbuffer bb;
+                uint32_t used = 0;
+                if (event_to_bitbuffer(buf.data() + at, sw.committed - at, 0, &bb, &used)) {
+                    fprintf(stderr, "host_core: corrupt event stream\n");
+                    abort();
+                }
+                at += used;
+                hc_event ev;
+                ev.package = h.pkgs.empty() ? 0xffffffffu : (uint32_t)(h.pkgs.size() - 1);
+                ev.dev = (uint32_t)i;
+                ev.ret = 0;
+                ev.hash = fnv1a(&bb, sizeof(bb));
+                ev.bb_idx = 0xffffffffu;
+                if (h.store_bitbuffers) {
+                    ev.bb_idx = (uint32_t)h.bbs.size();
+                    h.bbs.push_back(bb);
+                }
+                h.evts.push_back(ev);
+                if (!h.pkgs.empty()) h.pkgs.back().num_events++;
+            }
+        }
+    }
+}
+
+} // namespace
+
+extern "C" {
+
+void *hc_create() { return new Hc(); }
+void hc_destroy(void *p) { delete (Hc *)p; }
+void hc_set_capture(void *p, int store_bitbuffers, int store_stages)
+{
+    ((Hc *)p)->store_bitbuffers = store_bitbuffers;
+    ((Hc *)p)->store_stages = store_stages;
+}
+void hc_set_levels(void *p, int use_mag, float level_limit, float min_level, float min_snr)
+{
+    Hc *h = (Hc *)p;
+    h->use_mag = use_mag;
+    h->level_limit = level_limit;
+    h->min_level = min_level;
+    h->min_snr = min_snr;
+}
+void hc_set_fm_low_pass(void *p, float v) { ((Hc *)p)->fm_low_pass = v; }
+int hc_add_device(void *p, r433b_device const *d)
+{
+    Hc *h = (Hc *)p;
+    h->devs.push_back(*d);
+    return (int)h->devs.size() - 1;
+}
+
+int hc_run_stream(void *p, void const *iq, size_t bytes, int SS, uint32_t rate, uint32_t center, int fpdm_mode,
+        uint32_t block_bytes)
+{
+    Hc &h = *(Hc *)p;
+    h.pkgs.clear();
+    h.evts.clear();
+    h.bbs.clear();
+    h.ppool.clear();
+    h.gpool.clear();
+    h.am.clear();
+    h.fm.clear();
+    if (!block_bytes) block_bytes = 262144;
+    unsigned const block = block_bytes / SS;
+    unsigned long long const N = bytes / SS;
+    unsigned long long const n_blocks = (N + block - 1) / block;
+    Levels lv = compute_levels(h.use_mag, h.level_limit, h.min_level, h.min_snr);
+    int fpdm = fpdm_mode == 2 ? (center > 800000000u ? 1 : 0) : fpdm_mode;
+    int enable_fm = 0;
+    for (auto const &d : h.devs)
+        if (d.modulation >= 16) enable_fm = 1;
+    int const a1 = ((int)(0.85408 * 32768)) >> 1, b0 = ((int)(0.07296 * 32768)) >> 1;
+    int fa1 = 0, fb0 = 0;
+    if (enable_fm) fm_coeffs(SS == 4, rate, h.fm_low_pass != 0.0f ? h.fm_low_pass : fpdm ? 0.2f : 0.1f, fa1, fb0);
+
+    std::vector<int> scratch(4 * kMaxPulses, 0x5a5a5a5a); // deliberately dirty, like device scratch
+    Trains tr{scratch.data(), scratch.data() + kMaxPulses, scratch.data() + 2 * kMaxPulses, scratch.data() + 3 * kMaxPulses};
+    HostCtx cx;
+    DetState d;
+    det_reset(d);
+    d.ook_hw = d.fsk_hw = kMaxPulses;
+    int const per_ms = (int)(rate / 1000);
+    int y_am = 0, y_fm = 0, x_prev = 0, xf_prev = 0, pr = 0, pq = 0;
+
+    // a restatement of the package-emission arithmetic of k_detect (r433b_kernels.cuh, `emit`)
+    auto emit = [&](int type, unsigned long long pos, bool flush) {
+        PackageHeader ph = package_header(d, type);
+        unsigned cnt = ph.num_pulses + 1 < (unsigned)kMaxPulses ? ph.num_pulses + 1 : (unsigned)kMaxPulses;
+        unsigned long long blk = flush ? n_blocks : pos / block;
+        unsigned long long bstart = blk * block;
+        unsigned long long blen = flush ? 0 : (N - bstart < block ? N - bstart : block);
+        hc_package k;
+        memset(&k, 0, sizeof(k));
+        k.type = type;
+        k.block = (int)blk;
+        k.offset = ph.offset;
+        k.sample_rate = rate;
+        k.start_ago = flush ? (unsigned)(N - ph.start_abs) : (unsigned)(bstart + blen - ph.start_abs);
+        k.end_ago = flush ? 0u : (unsigned)(blen - (pos - bstart));
+        k.num_pulses = ph.num_pulses;
+        k.ook_low_estimate = ph.low;
+        k.ook_high_estimate = ph.high;
+        k.fsk_f1_est = ph.f1;
+        k.fsk_f2_est = ph.f2;
+        int const *sp = type == 1 ? tr.ook_pulse : tr.fsk_pulse;
+        int const *sg = type == 1 ? tr.ook_gap : tr.fsk_gap;
+        k.pulse_off = (uint32_t)h.ppool.size();
+        k.pulse_count = cnt;
+        h.ppool.insert(h.ppool.end(), sp, sp + cnt);
+        h.gpool.insert(h.gpool.end(), sg, sg + cnt);
+        k.first_event = (uint32_t)h.evts.size();
+        h.pkgs.push_back(k);
+        std::vector<int> pc(sp, sp + cnt), gc(sg, sg + cnt);
+        slice_package(h, type, rate, pc.data(), gc.data(), ph.num_pulses);
+    };
+
+    uint8_t const *u8 = (uint8_t const *)iq;
+    int16_t const *s16 = (int16_t const *)iq;
+    for (unsigned long long n = 0; n < N;) {
+        if (n % block == 0) det_call_boundary(d, lv);
+        // sample maps + filters for sample n
+        int ci, cq, x;
+        if (SS == 2) {
+            int ri = u8[2 * n], rq = u8[2 * n + 1];
+            ci = ri - 128;
+            cq = rq - 128;
+            x = h.use_mag ? mag_cu8(ri, rq) : env_cu8(ri, rq);
+        } else {
+            ci = s16[2 * n];
+            cq = s16[2 * n + 1];
+            x = mag_cs16(ci, cq);
+        }
+        int xl = (n % block == 0) ? (int)(int16_t)x_prev : x_prev;
+        y_am = iir16(y_am, a1, b0, x + xl);
+        x_prev = x;
+        int f;
+        if (enable_fm) {
+            if (SS == 2) {
+                int xf = atan16(cq * pr - ci * pq, ci * pr + cq * pq);
+                y_fm = iir16(y_fm, fa1, fb0, xf + xf_prev);
+                xf_prev = xf;
+                f = y_fm;
+            } else {
+                long long re = (long long)ci * pr + (long long)cq * pq;
+                long long im = (long long)cq * pr - (long long)ci * pq;
+                int xf = atan32((int)(unsigned)(unsigned long long)im, (int)(unsigned)(unsigned long long)re);
+                y_fm = iir32(y_fm, fa1, fb0, (long long)xf + xf_prev);
+                xf_prev = xf;
+                f = y_fm >> 16;
+            }
+        } else {
+            f = (int)(int16_t)x;
+        }
+        pr = ci;
+        pq = cq;
+        int a = (int)(int16_t)y_am;
+        f = (int)(int16_t)f;
+        if (h.store_stages) {
+            h.am.push_back((int16_t)a);
+            h.fm.push_back((int16_t)f);
+        }
+        // the detector may hand back the same sample after a package
+        for (;;) {
+            int ev = det_step(d, lv, tr, a, f, n, per_ms, fpdm, cx);
+            if (!ev) break;
+            emit(ev, n, false);
+            det_call_boundary(d, lv);
+        }
+        ++n;
+    }
+    for (;;) {
+        int ev = det_flush(d, tr, fpdm);
+        if (!ev) break;
+        emit(ev, N, true);
+    }
+    return (int)h.pkgs.size();
+}
+
+// ---- a native r433b_event_fn that records what r433b_dispatch() hands to decoders ----------
+struct Collector {
+    std::vector<hc_event> ev;
+    std::vector<bitbuffer> bbs;
+    int store;
+};
+
+void *hc_collector_create(int store)
+{
+    Collector *c = new Collector();
+    c->store = store;
+    return c;
+}
+void hc_collector_destroy(void *c) { delete (Collector *)c; }
+void hc_collector_clear(void *c)
+{
+    ((Collector *)c)->ev.clear();
+    ((Collector *)c)->bbs.clear();
+}
+int hc_collect_cb(void *user, uint32_t package, uint32_t device, struct pulse_data const *pd, struct bitbuffer *bits)
+{
+    (void)pd;
+    Collector *c = (Collector *)user;
+    hc_event e;
+    e.package = package;
+    e.dev = device;
+    e.ret = 0;
+    e.hash = fnv1a(bits, sizeof(*bits));
+    e.bb_idx = 0xffffffffu;
+    if (c->store) {
+        e.bb_idx = (uint32_t)c->bbs.size();
+        c->bbs.push_back(*bits);
+    }
+    c->ev.push_back(e);
+    return 0;
+}
+size_t hc_collector_count(void *c) { return ((Collector *)c)->ev.size(); }
+void const *hc_collector_events(void *c) { return ((Collector *)c)->ev.data(); }
+void const *hc_collector_bitbuffers(void *c) { return ((Collector *)c)->bbs.data(); }
+
+size_t hc_num_packages(void *p) { return ((Hc *)p)->pkgs.size(); }
+size_t hc_num_events(void *p) { return ((Hc *)p)->evts.size(); }
+size_t hc_num_bitbuffers(void *p) { return ((Hc *)p)->bbs.size(); }
+size_t hc_num_stage(void *p) { return ((Hc *)p)->am.size(); }
+void const *hc_packages(void *p) { return ((Hc *)p)->pkgs.data(); }
+void const *hc_events(void *p) { return ((Hc *)p)->evts.data(); }
+void const *hc_bitbuffers(void *p) { return ((Hc *)p)->bbs.data(); }
+int32_t const *hc_pulse_pool(void *p) { return ((Hc *)p)->ppool.data(); }
+int32_t const *hc_gap_pool(void *p) { return ((Hc *)p)->gpool.data(); }
+int16_t const *hc_am(void *p) { return ((Hc *)p)->am.data(); }
+int16_t const *hc_fm(void *p) { return ((Hc *)p)->fm.data(); }
+
+} // extern "C"

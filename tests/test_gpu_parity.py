@@ -1,0 +1,146 @@
+"""-m gpu: the CUDA path (through the C ABI) against the oracle on the same seeded inputs.
+
+Oracle = oracle/r433_oracle.c (CPU restatement) and, when the prebuilt file travelled with the
+snapshot, oracle/_ref/libr433ref.so (the unmodified reference).  Everything integer is compared
+for equality: stage arrays, pulse widths, package headers, every bitbuffer (by FNV-1a of the
+whole 6604-byte struct) in the reference's dispatch order.  The only floats on the path
+(calc_rssi_snr, src/r_flow.c:35-64) are computed on the host with the reference's expressions and
+compared for equality too (same libm, same box); tolerance would be 1 ULP if libm differed.
+"""
+import numpy as np
+import pytest
+
+import helpers
+from oracle import orc, refh
+from rtl_433_b200 import lib, synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def devices():
+    return lib.default_device_table()
+
+
+@pytest.fixture(scope="module")
+def ctx(devices):
+    c = lib.Context(0)
+    c.set_devices(devices)
+    yield c
+    c.close()
+
+
+def run_gpu(ctx, streams, fmt, rate, freq, fpdm=lib.FPDM_AUTO, block_bytes=0):
+    lens = [s.nbytes for s in streams]
+    padded = [(n + 15) // 16 * 16 for n in lens]
+    # the ABI wants 16-byte aligned stream starts; stream i is exactly lens[i] bytes long only
+    # when that is already a multiple of 16, so tests use such lengths
+    assert lens == padded
+    offsets = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
+    data = np.concatenate([s.view(np.uint8).ravel() for s in streams]) if streams else np.zeros(0, np.uint8)
+    ctx.process(data, offsets, fmt, rate, freq, fpdm, block_bytes, want_stages=True)
+    ctx.fetch()
+    out = []
+    for i, s in enumerate(streams):
+        r = helpers.gpu_stream_results(ctx, i)
+        n = lens[i] // fmt
+        r["am"], r["fm"] = ctx.copy_stage(i, n)
+        out.append(r)
+    return out
+
+
+def oracle_for(devices, stages=True):
+    o = orc.Oracle(store_bitbuffers=False, store_stages=stages)
+    o.add_devices(devices)
+    return o
+
+
+def check(gpu, ref, tag):
+    d = helpers.compare_results(ref, gpu, tag)
+    assert not d, "\n".join(d[:20])
+
+
+def test_ook_cu8_default_devices(ctx, devices):
+    """BASELINE config 2 at test size: noisy 250 kS/s cu8 streams, all 335 default decoders."""
+    streams = [synth.ook_stream(seed) for seed in range(6)]
+    gpu = run_gpu(ctx, streams, lib.FMT_CU8, 250000, 433920000)
+    o = oracle_for(devices)
+    for i, s in enumerate(streams):
+        ref = o.run(s, 2)
+        assert len(ref["packages"]) >= 8
+        check(gpu[i], ref, f"ook seed {i}")
+
+
+def test_fsk_cs16_minmax_and_classic(ctx, devices):
+    """BASELINE config 3 at test size: 1.024 MS/s cs16 2-FSK, both FSK pulse detectors."""
+    streams = [synth.fsk_stream(seed) for seed in range(3)]
+    o = oracle_for(devices)
+    for fpdm, freq in ((lib.FPDM_AUTO, 868000000), (lib.FPDM_CLASSIC, 433920000)):
+        gpu = run_gpu(ctx, streams, lib.FMT_CS16, 1024000, freq, fpdm)
+        for i, s in enumerate(streams):
+            ref = o.run(s, 4, 1024000, freq, fpdm)
+            assert any(p["type"] == 2 for p in ref["packages"])
+            check(gpu[i], ref, f"fsk seed {i} fpdm {fpdm}")
+
+
+def test_silence_and_reference_vectors(ctx, devices):
+    """Constant 128/128 silence (the IIR sits on two different fixed points: the bracket rounds
+    cannot collapse and must fall back to exact propagation), the reference's own Nice Flor-s
+    vector (tests/rtl_tcp_serve.py) and the config-1 Silvercrest file."""
+    def pad(x):
+        n = (len(x) + 15) // 16 * 16
+        return np.concatenate([x, np.full(n - len(x), 128, np.uint8)])
+    streams = [pad(synth.nice_flor_s_file()), pad(synth.silvercrest_file()), pad(synth.silvercrest_file(noise_sigma=2.0)),
+               np.full(4096 * 2, 128, np.uint8), np.zeros(0, np.uint8)]
+    gpu = run_gpu(ctx, streams, lib.FMT_CU8, 250000, 433920000)
+    o = oracle_for(devices)
+    for i, s in enumerate(streams):
+        ref = o.run(s, 2) if len(s) else {"packages": [], "events": []}
+        check(gpu[i], ref, f"vector {i}")
+    # the decoder-facing bitbuffer of config 1: {33}7c2600020 x 4 from device 0 (Silvercrest)
+    r = helpers.gpu_stream_results(ctx, 1, store_bitbuffers=True)
+    bb = [e["bitbuffer"] for e in r["events"] if e["dev"] == 0][0]
+    assert int(bb["num_rows"]) == 4
+    assert [refh.row_hex(bb, k) for k in range(4)] == ["{33}7c2600020"] * 4
+
+
+def test_against_compiled_reference(ctx, devices):
+    """Same comparison against the unmodified reference when oracle/_ref travelled here."""
+    if not refh.available():
+        pytest.skip("oracle/_ref/libr433ref.so not present")
+    r = refh.Ref(store_bitbuffers=False, store_stages=True)
+    r.register_defaults()
+    streams = [synth.ook_stream(100 + seed) for seed in range(2)]
+    gpu = run_gpu(ctx, streams, lib.FMT_CU8, 250000, 433920000)
+    for i, s in enumerate(streams):
+        check(gpu[i], r.run(s, 2), f"ref ook {i}")
+    streams = [synth.fsk_stream(100)]
+    gpu = run_gpu(ctx, streams, lib.FMT_CS16, 1024000, 868000000)
+    check(gpu[0], r.run(streams[0], 4, 1024000, 868000000, 2), "ref fsk")
+
+
+def test_ragged_lengths_and_small_blocks(ctx, devices):
+    """Streams of different lengths (incl. partial last tile/block) and a non-default block
+    size: exercises the block-call emulation (eop flag, start_ago/end_ago, x[-1] int16 wrap)."""
+    base = synth.ook_stream(7)
+    cuts = [2 * 16 * 1000, 2 * 16 * 4097, 2 * 131072 + 2 * 16 * 3, 2 * 8 * 99991 // 16 * 16]
+    streams = [base[:c].copy() for c in cuts]
+    o = oracle_for(devices)
+    for bb in (0, 32768):
+        gpu = run_gpu(ctx, streams, lib.FMT_CU8, 250000, 433920000, block_bytes=bb)
+        for i, s in enumerate(streams):
+            check(gpu[i], o.run(s, 2, block_bytes=bb), f"ragged {i} block {bb}")
+
+
+def test_magnitude_mode_and_fixed_level(ctx, devices):
+    streams = [synth.ook_stream(11), synth.ook_stream(12)]
+    try:
+        for kw in (dict(use_mag_est=1), dict(level_limit=-10.0), dict(min_level=-20.0, min_snr=6.0)):
+            ctx.set_levels(**kw)
+            gpu = run_gpu(ctx, streams, lib.FMT_CU8, 250000, 433920000)
+            o = oracle_for(devices)
+            o.set_levels(**kw)
+            for i, s in enumerate(streams):
+                check(gpu[i], o.run(s, 2), f"levels {kw} {i}")
+    finally:
+        ctx.set_levels()
