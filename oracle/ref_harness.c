@@ -73,6 +73,7 @@ typedef struct refh {
     int n_devs;
     r_device **devs;
     int (**orig_fn)(r_device *, bitbuffer_t *);
+    unsigned *proto_num; /* DEVICES index + 1 (create_fn devices do not carry it) */
     /* capture options */
     int chain_decoders, store_bitbuffers, store_stages;
     /* results of the current stream */
@@ -232,7 +233,7 @@ REFH_EXPORT void refh_destroy(refh_t *h)
     if (!h) return;
     if (g_active == h) g_active = NULL;
     free(h->pkgs); free(h->evts); free(h->bbs); free(h->pulse_pool); free(h->gap_pool);
-    free(h->am); free(h->fm); free(h->json); free(h->devs); free(h->orig_fn);
+    free(h->am); free(h->fm); free(h->json); free(h->devs); free(h->orig_fn); free(h->proto_num);
     /* the cfg is left to the process (r_free_cfg tears down outputs we never created) */
     free(h);
 }
@@ -309,7 +310,9 @@ static int track(refh_t *h, r_device *p)
 {
     h->devs = realloc(h->devs, (h->n_devs + 1) * sizeof(*h->devs));
     h->orig_fn = realloc(h->orig_fn, (h->n_devs + 1) * sizeof(*h->orig_fn));
+    h->proto_num = realloc(h->proto_num, (h->n_devs + 1) * sizeof(*h->proto_num));
     h->devs[h->n_devs] = p;
+    h->proto_num[h->n_devs] = p->protocol_num;
     h->orig_fn[h->n_devs] = p->decode_fn;
     p->decode_fn = capture_cb;
     p->log_fn = sink_log;
@@ -325,7 +328,9 @@ REFH_EXPORT int refh_register(refh_t *h, int idx)
     size_t before = h->cfg.demod->r_devs.len;
     register_protocol(&h->cfg, &h->cfg.devices[idx], NULL);
     if (h->cfg.demod->r_devs.len != before + 1) return -1;
-    return track(h, h->cfg.demod->r_devs.elems[before]);
+    int t = track(h, h->cfg.demod->r_devs.elems[before]);
+    h->proto_num[t] = (unsigned)idx + 1;
+    return t;
 }
 
 /* register_all_protocols(cfg, 0) (src/r_api.c:294): everything with disabled == 0 */
@@ -385,6 +390,7 @@ REFH_EXPORT int refh_get_registered(refh_t *h, int idx, refh_devinfo *out)
 {
     if (idx < 0 || idx >= h->n_devs) return -1;
     fill_info(out, h->devs[idx]);
+    out->protocol_num = h->proto_num[idx];
     return 0;
 }
 
@@ -572,6 +578,33 @@ REFH_EXPORT int refh_slice(refh_t *h, int dev_idx, int fsk, uint32_t sample_rate
     else
         run_ook_demods(&one, &pd);
     free(one.elems);
+    g_active = NULL;
+    return (int)h->n_evts;
+}
+
+/* run_ook_demods()/run_fsk_demods() over ALL registered devices on a caller-built pulse train */
+REFH_EXPORT int refh_slice_all(refh_t *h, int fsk, uint32_t sample_rate, uint32_t num_pulses,
+        int32_t const *pulse, int32_t const *gap)
+{
+    static pulse_data_t pd;
+    memset(&pd, 0, sizeof(pd));
+    pd.sample_rate = sample_rate;
+    pd.num_pulses = num_pulses;
+    memcpy(pd.pulse, pulse, num_pulses * sizeof(int32_t));
+    memcpy(pd.gap, gap, num_pulses * sizeof(int32_t));
+    clear_results(h);
+    g_active = h;
+    h->pkgs = grow(h->pkgs, &h->cap_pkgs, 1, sizeof(*h->pkgs));
+    memset(&h->pkgs[0], 0, sizeof(h->pkgs[0]));
+    h->n_pkgs = 1;
+    list_t all = {0};
+    list_ensure_size(&all, (size_t)h->n_devs + 1);
+    for (int i = 0; i < h->n_devs; ++i) list_push(&all, h->devs[i]);
+    if (fsk)
+        run_fsk_demods(&all, &pd);
+    else
+        run_ook_demods(&all, &pd);
+    free(all.elems);
     g_active = NULL;
     return (int)h->n_evts;
 }

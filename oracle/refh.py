@@ -98,6 +98,7 @@ def lib():
         L.refh_device_stats.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_uint32)]
         L.refh_abi_facts.argtypes = [C.POINTER(C.c_uint32)]
         L.refh_slice.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]
+        L.refh_slice_all.argtypes = [C.c_void_p, C.c_int, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]
         L.refh_envelope_detect.restype = C.c_float
         L.refh_envelope_detect.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
         L.refh_magnitude_est_cu8.restype = C.c_float
@@ -227,6 +228,22 @@ class Ref:
             return []
         addr = L.refh_bitbuffers(h)
         return list(np.frombuffer((C.c_uint8 * (nbb * 6604)).from_address(addr), dtype=BITBUFFER_DTYPE).copy())[:n]
+
+
+def _slice_all(self, fsk, sample_rate, pulse, gap):
+    """All registered devices on one pulse train -> [(dev, bitbuffer record)] in dispatch order."""
+    pulse = np.ascontiguousarray(pulse, np.int32)
+    gap = np.ascontiguousarray(gap, np.int32)
+    L, h = self.L, self.h
+    n = L.refh_slice_all(h, int(fsk), sample_rate, len(pulse), pulse.ctypes.data, gap.ctypes.data)
+    if not n:
+        return []
+    ev = L.refh_events(h)
+    bbs = np.frombuffer((C.c_uint8 * (n * 6604)).from_address(L.refh_bitbuffers(h)), dtype=BITBUFFER_DTYPE).copy()
+    return [(ev[i].dev, bbs[ev[i].bb_idx]) for i in range(n)]
+
+
+Ref.slice_all = _slice_all
 
 
 def row_hex(bb, row):

@@ -276,6 +276,27 @@ int hc_run_stream(void *p, void const *iq, size_t bytes, int SS, uint32_t rate, 
     return (int)h.pkgs.size();
 }
 
+// run the slicers of the registered devices on a caller-built pulse train (slicer unit tests)
+int hc_slice(void *p, int type, uint32_t rate, uint32_t n, int32_t const *pulse, int32_t const *gap)
+{
+    Hc &h = *(Hc *)p;
+    h.pkgs.clear();
+    h.evts.clear();
+    h.bbs.clear();
+    h.ppool.clear();
+    h.gpool.clear();
+    hc_package k;
+    memset(&k, 0, sizeof(k));
+    k.type = type;
+    k.num_pulses = n;
+    h.pkgs.push_back(k);
+    std::vector<int> pc(pulse, pulse + n), gc(gap, gap + n);
+    pc.push_back(0); // the entry after the last pulse is part of a package record (zeroed train)
+    gc.push_back(0);
+    slice_package(h, type, rate, pc.data(), gc.data(), n);
+    return (int)h.evts.size();
+}
+
 // ---- a native r433b_event_fn that records what r433b_dispatch() hands to decoders ----------
 struct Collector {
     std::vector<hc_event> ev;
