@@ -286,18 +286,26 @@ __global__ void __launch_bounds__(kDetectWarps * 32) k_detect(DetectParams p)
         int const a1 = p.lpf_a1, b0 = p.lpf_b0;
         long long const fa1 = p.fm_a1, fb0 = p.fm_b0;
 
-        auto run_chunk = [&](int &ya, int &yf) {
+        // both ends of both brackets advance together: four independent dependency chains
+        auto run_chunk2 = [&](int &ya0, int &ya1, int &yf0, int &yf1) {
             int xp = xl, fp = fl;
 #pragma unroll
             for (int k = 0; k < C; ++k) {
                 if (k < nv) {
-                    ya = iir16(ya, a1, b0, xs[k] + xp);
+                    int xsum = xs[k] + xp;
+                    ya0 = iir16(ya0, a1, b0, xsum);
+                    ya1 = iir16(ya1, a1, b0, xsum);
                     xp = xs[k];
                     if (fm_on) {
-                        if (SS == 2)
-                            yf = iir16(yf, (int)fa1, (int)fb0, xfv[k] + fp);
-                        else
-                            yf = iir32(yf, fa1, fb0, (long long)xfv[k] + fp);
+                        if (SS == 2) {
+                            int fsum = xfv[k] + fp;
+                            yf0 = iir16(yf0, (int)fa1, (int)fb0, fsum);
+                            yf1 = iir16(yf1, (int)fa1, (int)fb0, fsum);
+                        } else {
+                            long long fsum = (long long)xfv[k] + fp;
+                            yf0 = iir32(yf0, fa1, fb0, fsum);
+                            yf1 = iir32(yf1, fa1, fb0, fsum);
+                        }
                         fp = xfv[k];
                     }
                 }
@@ -320,8 +328,7 @@ __global__ void __launch_bounds__(kDetectWarps * 32) k_detect(DetectParams p)
             bool trust = p.wrap_free ? mine : (lane <= round);
             if (__all_sync(0xffffffffu, trust)) break;
             int ea_lo = lo_a, ea_hi = hi_a, ef_lo = lo_f, ef_hi = hi_f;
-            run_chunk(ea_lo, ef_lo);
-            run_chunk(ea_hi, ef_hi);
+            run_chunk2(ea_lo, ea_hi, ef_lo, ef_hi);
             int na_lo = __shfl_up_sync(0xffffffffu, ea_lo, 1);
             int na_hi = __shfl_up_sync(0xffffffffu, ea_hi, 1);
             int nf_lo = __shfl_up_sync(0xffffffffu, ef_lo, 1);
@@ -396,7 +403,140 @@ __global__ void __launch_bounds__(kDetectWarps * 32) k_detect(DetectParams p)
 
         // ---- package detector over the tile (warp-uniform) -------------------------------
         if (t0 % p.block_samples == 0) det_call_boundary(d, p.lv);
+
+        // Warp-cooperative fast paths.  Each looks at up to 32 consecutive samples (one per
+        // lane), proves with a ballot that the state machine stays on one simple trajectory for
+        // a prefix of them, and advances the (warp-uniform) state over that prefix at once.
+        // They return the number of samples consumed; 0 hands the current sample to det_step().
+
+        // IDLE: only the noise-floor tracker moves (src/pulse_detect.c:325-334).  While
+        // |am - low| < 1024 it is low += (am > low) ? +1 : -1; with q = low + j that is
+        // q += 2 * (am_j + j > q): two dependent instructions per sample.
+        auto idle_fast = [&](int n) -> int {
+            int cnt = nv_tile - n < 32 ? nv_tile - n : 32;
+            int hs = p.lv.ratio * d.low;
+            if (hs < p.lv.min_high) hs = p.lv.min_high;
+            if (d.high != hs) return 0; // first IDLE sample after a package: not yet re-derived
+            int a = lane < cnt ? (int)am_s[tile_index<C>(n + lane)] : -32768;
+            int lmin = d.low - cnt;
+            int hmin = p.lv.ratio * lmin;
+            if (hmin < p.lv.min_high) hmin = p.lv.min_high;
+            Thresholds th = det_thresholds(lmin, hmin, p.lv); // lowest trigger level reachable in this chunk
+            bool armed = d.lead_in + cnt - 1 > kLeadIn;
+            bool stop = lane < cnt && ((armed && a > th.up) || (a - lmin >= 1024) || (d.low + cnt - a >= 1024));
+            unsigned m = __ballot_sync(0xffffffffu, stop);
+            if (m) {
+                int first = __ffs(m) - 1;
+                cnt = first < cnt ? first : cnt;
+            }
+            if (cnt == 0) return 0;
+            int q = d.low;
+            int b = a + lane;
+#pragma unroll 8
+            for (int j = 0; j < cnt; ++j) {
+                int bj = __shfl_sync(0xffffffffu, b, j);
+                if (bj > q) q += 2;
+            }
+            d.low = q - cnt;
+            int hh = p.lv.ratio * d.low;
+            d.high = hh < p.lv.min_high ? p.lv.min_high : hh;
+            int li = d.lead_in + cnt;
+            d.lead_in = li > kLeadIn + 1 ? kLeadIn + 1 : li;
+            return cnt;
+        };
+
+        // GAP: thresholds are frozen; the next event is the first sample above `up` or the run
+        // length reaching an end-of-package limit (src/pulse_detect.c:422-470).
+        auto gap_fast = [&](int n) -> int {
+            if (d.eop_flag) return 0;
+            int cnt = nv_tile - n < 32 ? nv_tile - n : 32;
+            Thresholds th = det_thresholds(d.low, d.high, p.lv);
+            int a = lane < cnt ? (int)am_s[tile_index<C>(n + lane)] : -32768;
+            unsigned m = __ballot_sync(0xffffffffu, lane < cnt && a > th.up);
+            int ja = m ? __ffs(m) - 1 : 32;
+            long long lim_a = 10ll * d.longest > 10ll * per_ms ? 10ll * d.longest : 10ll * per_ms;
+            long long lim_b = 100ll * per_ms;
+            long long rstar = (lim_a < lim_b ? lim_a : lim_b) + 1; // first run length that ends the package
+            long long je = rstar - d.run - 1;
+            if (je < 0) je = 0;
+            if (ja < cnt && ja <= je) { // a new pulse starts first
+                d.run += ja + 1;
+                put(tr.ook_gap, d.ook_hw, d.ook_n, d.run);
+                d.ook_n += 1;
+                if (d.ook_n >= (unsigned)kMaxPulses) {
+                    d.st = kIdle;
+                    emit(1, t0 + n + ja, false);
+                    det_call_boundary(d, p.lv);
+                    return ja; // that sample is looked at again in IDLE
+                }
+                d.run = 0;
+                d.st = kPulse;
+                return ja + 1;
+            }
+            if (je < cnt) { // end of package by gap length
+                d.run += (int)je + 1;
+                put(tr.ook_gap, d.ook_hw, d.ook_n, d.run);
+                d.ook_n += 1;
+                d.st = kIdle;
+                emit(1, t0 + n + (int)je, false);
+                det_call_boundary(d, p.lv);
+                return (int)je;
+            }
+            d.run += cnt;
+            return cnt;
+        };
+
+        // PULSE after the first pulse (no FSK sub-detector): run the high-level and carrier
+        // estimators (src/pulse_detect.c:362-365) speculatively over the chunk, remember their
+        // value in front of every sample, then let every lane test its own sample against the
+        // threshold that value implies.  Everything before the first "below" is exact.
+        auto pulse_fast = [&](int n) -> int {
+            if (d.ook_n == 0) return 0;
+            int cnt = nv_tile - n < 32 ? nv_tile - n : 32;
+            int a = lane < cnt ? (int)am_s[tile_index<C>(n + lane)] : 32767;
+            int f = lane < cnt ? (int)fm_s[tile_index<C>(n + lane)] : 0;
+            int aq = a / 64, fq = f / 64;
+            int h = d.high, g = d.ook_f1;
+            int myh = h, myg = g;
+#pragma unroll 8
+            for (int j = 0; j < cnt; ++j) {
+                if (lane == j) {
+                    myh = h;
+                    myg = g;
+                }
+                int aj = __shfl_sync(0xffffffffu, aq, j);
+                int fj = __shfl_sync(0xffffffffu, fq, j);
+                h += aj - h / 64;
+                if (h < p.lv.min_high) h = p.lv.min_high;
+                g += fj - g / 64;
+            }
+            Thresholds th = det_thresholds(d.low, myh, p.lv);
+            unsigned m = __ballot_sync(0xffffffffu, lane < cnt && a < th.down);
+            if (!m) {
+                d.high = h;
+                d.ook_f1 = g;
+                d.run += cnt;
+                return cnt;
+            }
+            int jb = __ffs(m) - 1;
+            d.high = __shfl_sync(0xffffffffu, myh, jb);
+            d.ook_f1 = __shfl_sync(0xffffffffu, myg, jb);
+            d.run += jb;
+            return jb; // sample jb ends the pulse: det_step() takes it
+        };
+
         for (int n = 0; n < nv_tile;) {
+            int adv = 0;
+            if (d.st == kIdle)
+                adv = idle_fast(n);
+            else if (d.st == kGap)
+                adv = gap_fast(n);
+            else if (d.st == kPulse)
+                adv = pulse_fast(n);
+            if (adv) {
+                n += adv;
+                continue;
+            }
             int idx = tile_index<C>(n);
             int a = am_s[idx];
             int f = fm_s[idx];
