@@ -294,10 +294,10 @@ int r433b_process(r433b_ctx *ctx, r433b_batch const *b)
         if (b->n_streams) {
             unsigned grid = (b->n_streams + kDetectWarps - 1) / kDetectWarps;
             if (SS == 2) {
-                size_t sm = (size_t)kDetectWarps * 2 * TileCfg<2>::kTileHalf * sizeof(int16_t);
+                size_t sm = (size_t)kDetectWarps * TileCfg<2>::kTileWords * sizeof(uint32_t);
                 k_detect<2><<<grid, kDetectWarps * 32, sm, st>>>(dp);
             } else {
-                size_t sm = (size_t)kDetectWarps * 2 * TileCfg<4>::kTileHalf * sizeof(int16_t);
+                size_t sm = (size_t)kDetectWarps * TileCfg<4>::kTileWords * sizeof(uint32_t);
                 k_detect<4><<<grid, kDetectWarps * 32, sm, st>>>(dp);
             }
             CU(cudaGetLastError());
@@ -324,7 +324,11 @@ int r433b_process(r433b_ctx *ctx, r433b_batch const *b)
         if (device_takes((int)ctx->devs[i].modulation, 2)) fsk.push_back(i);
     }
     auto by_mod = [&](unsigned a, unsigned c) {
-        if (ctx->devs[a].modulation != ctx->devs[c].modulation) return ctx->devs[a].modulation < ctx->devs[c].modulation;
+        // lanes of a warp should walk the same code: same slicer, then similar event cadence
+        r433b_device const &x = ctx->devs[a], &y = ctx->devs[c];
+        if (x.modulation != y.modulation) return x.modulation < y.modulation;
+        if (x.reset_limit != y.reset_limit) return x.reset_limit < y.reset_limit;
+        if (x.short_width != y.short_width) return x.short_width < y.short_width;
         return a < c;
     };
     std::sort(ook.begin(), ook.end(), by_mod);

@@ -80,43 +80,45 @@ inline SlicerParams scale_device(r433b_device const &d, uint32_t rate)
 // One event of a pair's byte stream back into the decoder-facing struct
 // (include/bitbuffer.h:34-40).  Row r's bytes go to bb + r*128 and may run on into the
 // following rows exactly as the reference's spill-over does (src/bitbuffer.c:39-54).
-inline int event_to_bitbuffer(uint8_t const *ev, uint32_t pair_bytes, uint32_t index, struct bitbuffer *out,
+inline int event_to_bitbuffer(uint8_t const *ev8, uint32_t pair_bytes, uint32_t index, struct bitbuffer *out,
         uint32_t *consumed)
 {
-    if (!ev || !out) return -1;
+    if (!ev8 || !out || (pair_bytes & 3)) return -1;
+    uint32_t const *ev = reinterpret_cast<uint32_t const *>(ev8);
+    uint32_t const total = pair_bytes / 4;
     uint32_t pos = 0;
     for (uint32_t i = 0;; ++i) {
-        if (pos + kEventHdr > pair_bytes) return -1;
-        uint32_t num_rows = ev[pos] | (ev[pos + 1] << 8);
-        uint32_t free_row = ev[pos + 2] | (ev[pos + 3] << 8);
-        uint32_t len = ev[pos + 4] | (ev[pos + 5] << 8) | (ev[pos + 6] << 16) | ((uint32_t)ev[pos + 7] << 24);
-        if (len < (uint32_t)kEventHdr || pos + len > pair_bytes) return -1;
+        if (pos + 1 > total) return -1;
+        uint32_t h = ev[pos];
+        uint32_t num_rows = h & 0x7f, dirty = (h >> 7) & 1, free_row = (h >> 8) & 0xff, len = h >> 16;
+        if (len < 1 || pos + len > total) return -1;
         if (i == index) {
             memset(out, 0, sizeof(*out));
             out->num_rows = (uint16_t)num_rows;
             out->free_row = (uint16_t)free_row;
-            uint32_t q = pos + kEventHdr;
+            uint32_t q = pos + 1;
+            uint32_t const end = pos + len;
             uint8_t *flat = &out->bb[0][0];
             for (uint32_t r = 0; r < num_rows && r < R433B_BITBUF_ROWS; ++r) {
-                if (q + kRowHdr > pos + len) return -1;
-                uint32_t bits = ev[q] | (ev[q + 1] << 8);
-                uint32_t syncs = ev[q + 2] | (ev[q + 3] << 8);
-                uint32_t nb = ev[q + 4] | (ev[q + 5] << 8);
-                q += kRowHdr;
-                if (q + nb > pos + len) return -1;
+                if (q + 1 > end) return -1;
+                uint32_t bits = ev[q] & 0xffff, syncs = ev[q] >> 16;
+                q += 1;
+                uint32_t words = (bits + 31) / 32;
+                if (dirty && r + 1 == num_rows) words = ev[end - 1];
+                if (q + words > end) return -1;
                 out->bits_per_row[r] = (uint16_t)bits;
                 out->syncs_before_row[r] = (uint16_t)syncs;
                 size_t at = (size_t)r * R433B_BITBUF_COLS;
                 size_t room = sizeof(out->bb) - at;
+                size_t nb = (size_t)words * 4;
                 memcpy(flat + at, ev + q, nb < room ? nb : room);
-                q += nb;
+                q += words;
             }
-            if (consumed) *consumed = pos + len;
+            if (consumed) *consumed = (pos + len) * 4;
             return 0;
         }
         pos += len;
     }
 }
-
 
 } // namespace r433b

@@ -30,7 +30,6 @@ namespace r433b {
 
 constexpr int kTrainInts = 4 * kMaxPulses; // per-stream scratch: ook pulse/gap, fsk pulse/gap
 constexpr int kDetectWarps = 4;            // warps (streams) per CTA
-constexpr int kPadHalf = 8;                // shared-memory chunk padding, in int16 units
 
 struct DetectParams {
     uint8_t const *data;
@@ -56,10 +55,15 @@ struct WarpCtx {
     __device__ __forceinline__ void sync() { __syncwarp(); }
 };
 
-template <int C>
-__device__ __forceinline__ int tile_index(int n)
+// Shared-memory tile of one warp: sample n of the tile lives at word (n / C) * (W*C + 1) + (n % C) * W.
+// The odd chunk stride makes both access patterns conflict-free: every lane walking its own
+// chunk (IIR passes) and 32 lanes reading 32 consecutive samples (detector scans).
+// Word 0 of a sample holds envelope | discriminator << 16 (cu8) and later AM | FM << 16;
+// cs16 keeps its 32-bit discriminator output in word 1.
+template <int C, int W>
+__device__ __forceinline__ int word_index(int n)
 {
-    return n + (n / C) * kPadHalf;
+    return (n / C) * (W * C + 1) + (n % C) * W;
 }
 
 // ------------------------------------------------------------------------ k_detect ------
@@ -68,7 +72,8 @@ template <int SS>
 struct TileCfg {
     static constexpr int C = SS == 2 ? 32 : 16; // samples per lane per tile (64 bytes of IQ)
     static constexpr int T = 32 * C;
-    static constexpr int kTileHalf = 32 * (C + kPadHalf); // int16 slots per stage array
+    static constexpr int W = SS == 2 ? 1 : 2;   // shared-memory words per sample
+    static constexpr int kTileWords = 32 * (W * C + 1);
 };
 
 template <int SS>
@@ -77,15 +82,16 @@ __global__ void __launch_bounds__(kDetectWarps * 32) k_detect(DetectParams p)
     using Cfg = TileCfg<SS>;
     constexpr int C = Cfg::C;
     constexpr int T = Cfg::T;
-    extern __shared__ __align__(16) int16_t smem[];
+    constexpr int W = Cfg::W;
+    extern __shared__ __align__(16) uint32_t smem[];
 
     int const warp = threadIdx.x >> 5;
     int const lane = threadIdx.x & 31;
     unsigned const s = blockIdx.x * kDetectWarps + warp;
     if (s >= p.n_streams) return;
 
-    int16_t *am_s = smem + warp * 2 * Cfg::kTileHalf;
-    int16_t *fm_s = am_s + Cfg::kTileHalf;
+    uint32_t *tile = smem + warp * Cfg::kTileWords;
+    bool const fm_on = p.enable_fm != 0;
 
     unsigned long long const byte0 = p.offsets[s];
     unsigned long long const N = (p.offsets[s + 1] - byte0) / SS;
@@ -169,144 +175,123 @@ __global__ void __launch_bounds__(kDetectWarps * 32) k_detect(DetectParams p)
         int nv = nv_tile - lane * C; // valid samples in this lane's chunk
         nv = nv < 0 ? 0 : (nv > C ? C : nv);
 
-        // ---- load the lane's 64 bytes of IQ ------------------------------------------
-        uint32_t raw[16];
-        {
-            uint8_t const *g = src + (t0 + (unsigned long long)lane * C) * SS;
-            if (nv == C) {
-                uint4 const *g4 = reinterpret_cast<uint4 const *>(g);
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    uint4 v = __ldg(g4 + q);
-                    raw[4 * q + 0] = v.x;
-                    raw[4 * q + 1] = v.y;
-                    raw[4 * q + 2] = v.z;
-                    raw[4 * q + 3] = v.w;
-                }
-            } else {
-#pragma unroll
-                for (int q = 0; q < 16; ++q) {
-                    uint32_t w = 0;
-                    for (int b = 0; b < 4; ++b) {
-                        int byte = q * 4 + b;
-                        if (byte < nv * SS) w |= (uint32_t)g[byte] << (8 * b);
-                    }
-                    raw[q] = w;
-                }
+        // ---- phase 1: sample maps, coalesced ------------------------------------------------
+        // Iteration q: lane l takes the 16 contiguous bytes (8 cu8 / 4 cs16 samples) at
+        // q*512 + l*16 of the tile: one fully coalesced 128-bit load per lane.  Envelope x and
+        // phase-discriminator xf go to the warp's shared-memory tile.
+        constexpr int SPL = 16 / SS;          // samples per 128-bit load
+        constexpr int NQ = T / (32 * SPL);    // load iterations per tile (4)
+#pragma unroll 1
+        for (int q = 0; q < NQ; ++q) {
+            int const n0 = q * 32 * SPL + lane * SPL;
+            uint32_t rw[4] = {0u, 0u, 0u, 0u};
+            uint8_t const *g = src + (t0 + (unsigned long long)n0) * SS;
+            if (n0 + SPL <= nv_tile) {
+                uint4 v = __ldg(reinterpret_cast<uint4 const *>(g));
+                rw[0] = v.x;
+                rw[1] = v.y;
+                rw[2] = v.z;
+                rw[3] = v.w;
+            } else if (n0 < nv_tile) { // ragged end of the stream
+                int nb = (nv_tile - n0) * SS;
+                for (int bidx = 0; bidx < nb; ++bidx) rw[bidx >> 2] |= (uint32_t)g[bidx] << (8 * (bidx & 3));
             }
-        }
-
-        // ---- sample maps: envelope x[k] and discriminator xf[k] ------------------------
-        // previous IQ sample for the first sample of the chunk comes from the lane to the left
-        int xs[C];  // envelope (uint16 range)
-        int xfv[C]; // discriminator output (int16 for cu8, int32 for cs16); raw envelope if FM is off
-        {
-            int last_i, last_q;
+            int li, lq; // last sample of this lane's group, for the lane to the right
             if (SS == 2) {
-                last_i = (int)((raw[15] >> 16) & 0xff) - 128;
-                last_q = (int)((raw[15] >> 24) & 0xff) - 128;
+                li = (int)((rw[3] >> 16) & 0xff) - 128;
+                lq = (int)((rw[3] >> 24) & 0xff) - 128;
             } else {
-                last_i = (int)(int16_t)(raw[15] & 0xffff);
-                last_q = (int)(int16_t)(raw[15] >> 16);
+                li = (int)(int16_t)(rw[3] & 0xffff);
+                lq = (int)(int16_t)(rw[3] >> 16);
             }
-            int pi_ = __shfl_up_sync(0xffffffffu, last_i, 1);
-            int pq_ = __shfl_up_sync(0xffffffffu, last_q, 1);
+            int pi_ = __shfl_up_sync(0xffffffffu, li, 1);
+            int pq_ = __shfl_up_sync(0xffffffffu, lq, 1);
             if (lane == 0) {
                 pi_ = pr_prev;
                 pq_ = pi_prev;
             }
+            pr_prev = __shfl_sync(0xffffffffu, li, 31);
+            pi_prev = __shfl_sync(0xffffffffu, lq, 31);
 #pragma unroll
-            for (int k = 0; k < C; ++k) {
-                int ci, cq, ri, rq;
+            for (int j = 0; j < SPL; ++j) {
+                int ci, cq, x, xf;
                 if (SS == 2) {
-                    uint32_t w = raw[k >> 1];
-                    ri = (int)((w >> ((k & 1) * 16)) & 0xff);
-                    rq = (int)((w >> ((k & 1) * 16 + 8)) & 0xff);
+                    uint32_t w = rw[j >> 1];
+                    int ri = (int)((w >> ((j & 1) * 16)) & 0xff);
+                    int rq = (int)((w >> ((j & 1) * 16 + 8)) & 0xff);
                     ci = ri - 128;
                     cq = rq - 128;
-                    xs[k] = p.use_mag ? mag_cu8(ri, rq) : env_cu8(ri, rq);
+                    x = p.use_mag ? mag_cu8(ri, rq) : env_cu8(ri, rq);
                 } else {
-                    uint32_t w = raw[k];
+                    uint32_t w = rw[j];
                     ci = (int)(int16_t)(w & 0xffff);
                     cq = (int)(int16_t)(w >> 16);
-                    xs[k] = mag_cs16(ci, cq);
+                    x = mag_cs16(ci, cq);
                 }
-                if (p.enable_fm) {
+                if (fm_on) {
                     if (SS == 2) {
-                        int re = ci * pi_ + cq * pq_;
-                        int im = cq * pi_ - ci * pq_;
-                        xfv[k] = atan16(im, re);
+                        xf = atan16(cq * pi_ - ci * pq_, ci * pi_ + cq * pq_);
                     } else {
                         long long re = (long long)ci * pi_ + (long long)cq * pq_;
                         long long im = (long long)cq * pi_ - (long long)ci * pq_;
-                        xfv[k] = atan32((int)(unsigned)(unsigned long long)im, (int)(unsigned)(unsigned long long)re);
+                        xf = atan32((int)(unsigned)(unsigned long long)im, (int)(unsigned)(unsigned long long)re);
                     }
                 } else {
-                    xfv[k] = (int)(int16_t)xs[k];
+                    xf = (int)(int16_t)x; // buf.fm aliases the raw envelope when FM is off
                 }
                 pi_ = ci;
                 pq_ = cq;
-            }
-            // carry the last VALID sample of the tile to the next tile (lane 31 when full)
-            int src_lane = (nv_tile - 1) / C;
-            int kk = (nv_tile - 1) % C;
-            int li = 0, lq = 0;
-            {
-                int ci = 0, cq = 0;
-#pragma unroll
-                for (int k = 0; k < C; ++k) {
-                    if (k == kk) {
-                        if (SS == 2) {
-                            uint32_t w = raw[k >> 1];
-                            ci = (int)((w >> ((k & 1) * 16)) & 0xff) - 128;
-                            cq = (int)((w >> ((k & 1) * 16 + 8)) & 0xff) - 128;
-                        } else {
-                            ci = (int)(int16_t)(raw[k] & 0xffff);
-                            cq = (int)(int16_t)(raw[k] >> 16);
-                        }
-                    }
+                int at = word_index<C, W>(n0 + j);
+                if (W == 1) {
+                    tile[at] = (uint32_t)x | ((uint32_t)xf << 16);
+                } else {
+                    tile[at] = (uint32_t)x;
+                    tile[at + 1] = (uint32_t)xf;
                 }
-                li = __shfl_sync(0xffffffffu, ci, src_lane);
-                lq = __shfl_sync(0xffffffffu, cq, src_lane);
             }
-            pr_prev = li;
-            pi_prev = lq;
         }
+        __syncwarp();
 
-        // ---- the two IIR low-passes, exact and lane-parallel -----------------------------
-        // inputs to the first sample of the chunk: previous envelope / discriminator values
-        int xl = __shfl_up_sync(0xffffffffu, xs[C - 1], 1);
-        int fl = __shfl_up_sync(0xffffffffu, xfv[C - 1], 1);
+        // ---- phase 2: the two IIR low-passes, exact and lane-parallel -----------------------
+        // lane l owns samples [l*C, l*C + C) of the tile; nv of them exist
+        uint32_t *mine = tile + lane * (W * C + 1);
+        int xl, fl; // envelope / discriminator of the sample in front of the chunk
         if (lane == 0) {
             // the reference keeps x[-1] as int16 across block calls (src/baseband.c:167)
             xl = (t0 % p.block_samples == 0) ? (int)(int16_t)x_prev : x_prev;
             fl = xf_prev;
+        } else {
+            uint32_t const *left = mine - 1 - W; // last sample of the lane to the left
+            xl = (int)(left[0] & 0xffff);
+            fl = W == 1 ? (int)(int16_t)(left[0] >> 16) : (int)left[1];
         }
-        bool const fm_on = p.enable_fm != 0;
         int const a1 = p.lpf_a1, b0 = p.lpf_b0;
         long long const fa1 = p.fm_a1, fb0 = p.fm_b0;
 
         // both ends of both brackets advance together: four independent dependency chains
         auto run_chunk2 = [&](int &ya0, int &ya1, int &yf0, int &yf1) {
             int xp = xl, fp = fl;
-#pragma unroll
-            for (int k = 0; k < C; ++k) {
-                if (k < nv) {
-                    int xsum = xs[k] + xp;
-                    ya0 = iir16(ya0, a1, b0, xsum);
-                    ya1 = iir16(ya1, a1, b0, xsum);
-                    xp = xs[k];
-                    if (fm_on) {
-                        if (SS == 2) {
-                            int fsum = xfv[k] + fp;
-                            yf0 = iir16(yf0, (int)fa1, (int)fb0, fsum);
-                            yf1 = iir16(yf1, (int)fa1, (int)fb0, fsum);
-                        } else {
-                            long long fsum = (long long)xfv[k] + fp;
-                            yf0 = iir32(yf0, fa1, fb0, fsum);
-                            yf1 = iir32(yf1, fa1, fb0, fsum);
-                        }
-                        fp = xfv[k];
+#pragma unroll 4
+            for (int k = 0; k < nv; ++k) {
+                uint32_t w0 = mine[k * W];
+                int x = (int)(w0 & 0xffff);
+                int xsum = x + xp;
+                ya0 = iir16(ya0, a1, b0, xsum);
+                ya1 = iir16(ya1, a1, b0, xsum);
+                xp = x;
+                if (fm_on) {
+                    if (SS == 2) {
+                        int v = (int)(int16_t)(w0 >> 16);
+                        int fsum = v + fp;
+                        yf0 = iir16(yf0, (int)fa1, (int)fb0, fsum);
+                        yf1 = iir16(yf1, (int)fa1, (int)fb0, fsum);
+                        fp = v;
+                    } else {
+                        int v = (int)mine[k * W + 1];
+                        long long fsum = (long long)v + fp;
+                        yf0 = iir32(yf0, fa1, fb0, fsum);
+                        yf1 = iir32(yf1, fa1, fb0, fsum);
+                        fp = v;
                     }
                 }
             }
@@ -322,10 +307,11 @@ __global__ void __launch_bounds__(kDetectWarps * 32) k_detect(DetectParams p)
             lo_f = SS == 2 ? -32768 : (int)0x80000000;
             hi_f = SS == 2 ? 32767 : 0x7fffffff;
         }
+#pragma unroll 1
         for (int round = 0; round < 31; ++round) {
-            bool mine = (lo_a == hi_a) && (!fm_on || lo_f == hi_f);
+            bool mine_ok = (lo_a == hi_a) && (!fm_on || lo_f == hi_f);
             // lanes 0..round are exact by induction even if the filter could wrap
-            bool trust = p.wrap_free ? mine : (lane <= round);
+            bool trust = p.wrap_free ? mine_ok : (lane <= round);
             if (__all_sync(0xffffffffu, trust)) break;
             int ea_lo = lo_a, ea_hi = hi_a, ef_lo = lo_f, ef_hi = hi_f;
             run_chunk2(ea_lo, ea_hi, ef_lo, ef_hi);
@@ -341,58 +327,40 @@ __global__ void __launch_bounds__(kDetectWarps * 32) k_detect(DetectParams p)
             }
         }
 
-        // final pass from the exact state, writing the stage tile
+        // ---- phase 3: final pass from the exact state; AM|FM replace x|xf in place -----------
         {
             int ya = lo_a, yf = lo_f;
             int xp = xl, fp = fl;
-            int16_t *am_w = am_s + lane * (C + kPadHalf);
-            int16_t *fm_w = fm_s + lane * (C + kPadHalf);
-            uint32_t pack_a[C / 2], pack_f[C / 2];
-#pragma unroll
-            for (int k = 0; k < C; ++k) {
+            unsigned long long const gbase = sample0 + t0 + (unsigned long long)lane * C;
+#pragma unroll 4
+            for (int k = 0; k < nv; ++k) {
+                uint32_t w0 = mine[k * W];
+                int x = (int)(w0 & 0xffff);
+                ya = iir16(ya, a1, b0, x + xp);
+                xp = x;
                 int fo;
-                if (k < nv) {
-                    ya = iir16(ya, a1, b0, xs[k] + xp);
-                    xp = xs[k];
-                    if (fm_on) {
-                        if (SS == 2) {
-                            yf = iir16(yf, (int)fa1, (int)fb0, xfv[k] + fp);
-                            fo = yf;
-                        } else {
-                            yf = iir32(yf, fa1, fb0, (long long)xfv[k] + fp);
-                            fo = yf >> 16;
-                        }
-                        fp = xfv[k];
+                if (fm_on) {
+                    if (SS == 2) {
+                        int v = (int)(int16_t)(w0 >> 16);
+                        yf = iir16(yf, (int)fa1, (int)fb0, v + fp);
+                        fp = v;
+                        fo = yf;
                     } else {
-                        fo = xfv[k];
+                        int v = (int)mine[k * W + 1];
+                        yf = iir32(yf, fa1, fb0, (long long)v + fp);
+                        fp = v;
+                        fo = yf >> 16;
                     }
                 } else {
-                    fo = 0;
+                    fo = (int)(int16_t)x;
                 }
-                uint32_t av = (uint32_t)(uint16_t)(int16_t)ya;
-                uint32_t fv = (uint32_t)(uint16_t)(int16_t)fo;
-                if (k & 1) {
-                    pack_a[k >> 1] |= av << 16;
-                    pack_f[k >> 1] |= fv << 16;
-                } else {
-                    pack_a[k >> 1] = av;
-                    pack_f[k >> 1] = fv;
+                mine[k * W] = (uint32_t)(uint16_t)(int16_t)ya | ((uint32_t)(uint16_t)(int16_t)fo << 16);
+                if (p.am_out) {
+                    p.am_out[gbase + k] = (int16_t)ya;
+                    p.fm_out[gbase + k] = (int16_t)fo;
                 }
             }
-#pragma unroll
-            for (int q = 0; q < C / 8; ++q) {
-                reinterpret_cast<uint4 *>(am_w)[q] = make_uint4(pack_a[4 * q], pack_a[4 * q + 1], pack_a[4 * q + 2], pack_a[4 * q + 3]);
-                reinterpret_cast<uint4 *>(fm_w)[q] = make_uint4(pack_f[4 * q], pack_f[4 * q + 1], pack_f[4 * q + 2], pack_f[4 * q + 3]);
-            }
-            if (p.am_out) {
-                unsigned long long base = sample0 + t0 + (unsigned long long)lane * C;
-                for (int k = 0; k < nv; ++k) {
-                    p.am_out[base + k] = (int16_t)(pack_a[k >> 1] >> ((k & 1) * 16));
-                    p.fm_out[base + k] = (int16_t)(pack_f[k >> 1] >> ((k & 1) * 16));
-                }
-            }
-            // carries for the next tile: the state after the last valid sample (identity steps
-            // in lanes past the end make lane 31 hold it)
+            // carries for the next tile: the state after the last valid sample
             int last_lane = (nv_tile - 1) / C;
             y_am = __shfl_sync(0xffffffffu, ya, last_lane);
             y_fm = __shfl_sync(0xffffffffu, yf, last_lane);
@@ -417,7 +385,7 @@ __global__ void __launch_bounds__(kDetectWarps * 32) k_detect(DetectParams p)
             int hs = p.lv.ratio * d.low;
             if (hs < p.lv.min_high) hs = p.lv.min_high;
             if (d.high != hs) return 0; // first IDLE sample after a package: not yet re-derived
-            int a = lane < cnt ? (int)am_s[tile_index<C>(n + lane)] : -32768;
+            int a = lane < cnt ? (int)(int16_t)(tile[word_index<C, W>(n + lane)] & 0xffff) : -32768;
             int lmin = d.low - cnt;
             int hmin = p.lv.ratio * lmin;
             if (hmin < p.lv.min_high) hmin = p.lv.min_high;
@@ -451,7 +419,7 @@ __global__ void __launch_bounds__(kDetectWarps * 32) k_detect(DetectParams p)
             if (d.eop_flag) return 0;
             int cnt = nv_tile - n < 32 ? nv_tile - n : 32;
             Thresholds th = det_thresholds(d.low, d.high, p.lv);
-            int a = lane < cnt ? (int)am_s[tile_index<C>(n + lane)] : -32768;
+            int a = lane < cnt ? (int)(int16_t)(tile[word_index<C, W>(n + lane)] & 0xffff) : -32768;
             unsigned m = __ballot_sync(0xffffffffu, lane < cnt && a > th.up);
             int ja = m ? __ffs(m) - 1 : 32;
             long long lim_a = 10ll * d.longest > 10ll * per_ms ? 10ll * d.longest : 10ll * per_ms;
@@ -493,8 +461,9 @@ __global__ void __launch_bounds__(kDetectWarps * 32) k_detect(DetectParams p)
         auto pulse_fast = [&](int n) -> int {
             if (d.ook_n == 0) return 0;
             int cnt = nv_tile - n < 32 ? nv_tile - n : 32;
-            int a = lane < cnt ? (int)am_s[tile_index<C>(n + lane)] : 32767;
-            int f = lane < cnt ? (int)fm_s[tile_index<C>(n + lane)] : 0;
+            uint32_t wv = lane < cnt ? tile[word_index<C, W>(n + lane)] : 0x00007fffu;
+            int a = (int)(int16_t)(wv & 0xffff);
+            int f = (int)(int16_t)(wv >> 16);
             int aq = a / 64, fq = f / 64;
             int h = d.high, g = d.ook_f1;
             int myh = h, myg = g;
@@ -537,9 +506,9 @@ __global__ void __launch_bounds__(kDetectWarps * 32) k_detect(DetectParams p)
                 n += adv;
                 continue;
             }
-            int idx = tile_index<C>(n);
-            int a = am_s[idx];
-            int f = fm_s[idx];
+            uint32_t wv = tile[word_index<C, W>(n)];
+            int a = (int)(int16_t)(wv & 0xffff);
+            int f = (int)(int16_t)(wv >> 16);
             int ev = det_step(d, p.lv, tr, a, f, t0 + n, per_ms, p.fpdm, cx);
             if (ev) {
                 emit(ev, t0 + n, false);
@@ -595,44 +564,48 @@ __global__ void __launch_bounds__(kSliceThreads) k_slice(SliceParams p)
         unsigned slot = base + threadIdx.x;
         bool active = slot < n_list;
         unsigned dev = active ? list[slot] : 0;
-        unsigned bytes = 0, nev = 0;
-        SlicerParams sp;
-        if (active) {
-            sp = p.dev[dev];
-            EventWriter<false> cw;
-            cw.init(nullptr);
-            slice_dispatch(pv, sp, cw);
-            bytes = cw.committed;
-            nev = cw.events;
-        }
-        // warp-aggregated reservation in the event arena
-        unsigned incl = bytes;
         unsigned lane = threadIdx.x & 31;
+        unsigned bytes = 0, nev = 0;
+        unsigned long long off = 0;
+        bool fits = false;
+        SlicerParams sp;
+        if (active) sp = p.dev[dev];
+        // pass 0 counts, pass 1 stores; one copy of the slicer code serves both
+#pragma unroll 1
+        for (int pass = 0; pass < 2; ++pass) {
+            if (pass == 1) {
+                // warp-aggregated reservation in the event arena
+                unsigned incl = bytes;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            unsigned v = __shfl_up_sync(0xffffffffu, incl, o);
-            if ((int)lane >= o) incl += v;
-        }
-        unsigned total = __shfl_sync(0xffffffffu, incl, 31);
-        unsigned evs = nev;
+                for (int o = 1; o < 32; o <<= 1) {
+                    unsigned v = __shfl_up_sync(0xffffffffu, incl, o);
+                    if ((int)lane >= o) incl += v;
+                }
+                unsigned total = __shfl_sync(0xffffffffu, incl, 31);
+                unsigned evs = nev;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) evs += __shfl_xor_sync(0xffffffffu, evs, o);
-        unsigned long long wbase = 0;
-        if (lane == 0 && total) {
-            wbase = atomicAdd(p.cursor, (unsigned long long)total);
-            atomicAdd(p.cursor + 1, (unsigned long long)evs);
-        }
-        wbase = __shfl_sync(0xffffffffu, wbase, 0);
-        unsigned long long off = wbase + incl - bytes;
-        if (active) {
-            bool fits = off + bytes <= p.arena_cap;
-            if (bytes && fits) {
-                EventWriter<true> sw;
-                sw.init(p.arena + off, bytes);
-                slice_dispatch(pv, sp, sw);
-            } else if (bytes) {
-                atomicOr(p.cursor + 2, 1ull);
+                for (int o = 16; o > 0; o >>= 1) evs += __shfl_xor_sync(0xffffffffu, evs, o);
+                unsigned long long wbase = 0;
+                if (lane == 0 && total) {
+                    wbase = atomicAdd(p.cursor, (unsigned long long)total);
+                    atomicAdd(p.cursor + 1, (unsigned long long)evs);
+                }
+                wbase = __shfl_sync(0xffffffffu, wbase, 0);
+                off = wbase + incl - bytes;
+                fits = off + bytes <= p.arena_cap;
+                if (active && bytes && !fits) atomicOr(p.cursor + 2, 1ull);
             }
+            if (active && (pass == 0 || (bytes && fits))) {
+                EventWriter w;
+                w.init(pass ? reinterpret_cast<uint32_t *>(p.arena + off) : nullptr, bytes / 4);
+                slice_dispatch(pv, sp, w);
+                if (pass == 0) {
+                    bytes = w.committed * 4;
+                    nev = w.events;
+                }
+            }
+        }
+        if (active) {
             r433b_pair pr;
             pr.offset = off;
             pr.bytes = bytes;

@@ -6,13 +6,15 @@
 // 6604-byte bitbuffer_t (include/bitbuffer.h:34-40) per event, rows are streamed straight into
 // the pair's private output region in the wire format below; the host re-inflates a real
 // bitbuffer_t only when it calls a decoder (r433b_host.cpp).  Every run is executed twice by
-// the kernel: once with a counting writer (size), once with a storing writer.
+// the kernel: once counting (size), once storing.
 //
-//   event   := u16 num_rows, u16 free_row, u32 event_bytes (whole event incl. this header), row*
-//   row     := u16 bits, u16 syncs, u16 nbytes, u8 data[nbytes]      (physical row order)
+//   event   := u32 { num_rows:7, dirty:1, free_row:8, words:16 }   words = whole event incl. this
+//              row*  [u32 last_row_words  -- only if dirty]
+//   row     := u32 { bits:16, syncs:16 }  then ceil(bits/32) data words (physical row order;
+//              bit i of the row is bit (7 - i%8) of byte i/8, exactly bitbuffer_t's bb layout)
 //
-// `nbytes` can exceed ceil(bits/8) only after the reference's 50-row overflow path, which
-// zeroes a row's length but keeps its bytes (src/bitbuffer.c:118-121).
+// `dirty` marks the reference's 50-row overflow path, which zeroes the last row's length but
+// keeps its bytes (src/bitbuffer.c:118-121): the number of data words then comes from the trailer.
 #pragma once
 #include <stdint.h>
 #include "r433b_core.cuh"
@@ -21,8 +23,6 @@ namespace r433b {
 
 constexpr int kBbRows = 50;   // include/bitbuffer.h:28
 constexpr int kBbCols = 128;  // include/bitbuffer.h:27
-constexpr int kEventHdr = 8;
-constexpr int kRowHdr = 6;
 
 // float helpers: no fused multiply-add anywhere (the reference is built without contraction)
 #ifdef __CUDA_ARCH__
@@ -52,28 +52,30 @@ struct SlicerParams {
 
 // ----------------------------------------------------------------------------- writer ----
 
-template <bool STORE>
+// One writer type serves both passes: out == nullptr only counts.  All offsets are in 32-bit
+// words; every store is one aligned word.
 struct EventWriter {
-    uint8_t *out;       // pair region (STORE only)
-    unsigned limit;     // size of the region = bytes the counting pass committed (STORE only):
-                        // rows of a trailing, never-emitted event must not be written
-    unsigned pos;       // bytes committed by finished events + current event so far
-    unsigned committed; // bytes up to the end of the last emitted event
+    uint32_t *out;      // pair region, or nullptr while counting
+    unsigned limit;     // words the counting pass committed: rows of a trailing, never-emitted
+                        // event lie beyond it and must not be written
+    unsigned pos;       // words used by finished events + the current event so far
+    unsigned committed; // words up to the end of the last emitted event
     unsigned events;
     // current event
     unsigned ev_start;
     unsigned num_rows, free_row;
+    unsigned row0_bits; // bits_per_row[0] once row 0 is closed
     // current (last) row
-    unsigned row_hdr;   // offset of its header
-    unsigned bits, syncs, row_hw;
-    unsigned first_row_bits; // bits_per_row[0] of the current event
-    unsigned acc;       // partial byte being assembled
-    bool dirty;         // row length was reset while bytes stayed (overflow path)
+    unsigned row_hdr;   // word offset of its header
+    unsigned bits, syncs;
+    unsigned row_hw;    // data words that hold something
+    unsigned acc;       // word being assembled
+    bool dirty;         // row length was reset while its bytes stayed (50-row overflow path)
 
-    R4_HD void init(uint8_t *o, unsigned region_bytes = 0)
+    R4_HD void init(uint32_t *o, unsigned region_words = 0)
     {
         out = o;
-        limit = region_bytes;
+        limit = region_words;
         pos = committed = 0;
         events = 0;
         reset_event();
@@ -84,79 +86,75 @@ struct EventWriter {
         pos = committed;
         ev_start = committed;
         num_rows = free_row = 0;
+        row0_bits = 0;
         row_hdr = 0;
         bits = syncs = row_hw = 0;
-        first_row_bits = 0;
         acc = 0;
         dirty = false;
     }
 
-    R4_HD void put16(unsigned at, unsigned v)
+    R4_HD void put(unsigned at, uint32_t v)
     {
-        if (STORE && at + 1 < limit) {
-            out[at] = (uint8_t)v;
-            out[at + 1] = (uint8_t)(v >> 8);
-        }
+        if (out && at < limit) out[at] = v;
     }
+
+    R4_HD unsigned first_row_bits() const { return num_rows <= 1 ? bits : row0_bits; }
+    R4_HD unsigned last_row_bits() const { return bits; }
 
     R4_HD void open_row()
     {
         row_hdr = pos;
-        pos += kRowHdr;
+        pos += 1;
         bits = syncs = row_hw = 0;
         acc = 0;
-        dirty = false;
     }
 
-    R4_HD void flush_byte()
+    R4_HD void flush_word()
     {
-        // the byte that holds bit index (bits-1) .. is complete or the row is closing
-        unsigned j = (bits - 1) >> 3;
-        unsigned at = row_hdr + kRowHdr + j;
-        if (STORE && at < limit) {
-            if (j < row_hw)
-                out[at] |= (uint8_t)acc;
+        unsigned w = (bits - 1) >> 5; // the word holding the newest bit
+        unsigned at = row_hdr + 1 + w;
+        if (out && at < limit) {
+            if (w < row_hw)
+                out[at] |= acc;
             else
-                out[at] = (uint8_t)acc;
+                out[at] = acc;
         }
-        if (j + 1 > row_hw) row_hw = j + 1;
+        if (w + 1 > row_hw) row_hw = w + 1;
         acc = 0;
     }
 
     R4_HD void close_row()
     {
-        if (bits & 7) flush_byte();
-        put16(row_hdr, bits);
-        put16(row_hdr + 2, syncs);
-        put16(row_hdr + 4, row_hw);
-        pos = row_hdr + kRowHdr + row_hw;
+        if (bits & 31) flush_word();
+        put(row_hdr, bits | (syncs << 16));
+        pos = row_hdr + 1 + row_hw;
     }
 
     R4_HD void first_row() // "Add first row automatically", src/bitbuffer.c:24-26
     {
         if (num_rows == 0) {
             ev_start = pos;
-            pos += kEventHdr;
+            pos += 1;
             num_rows = free_row = 1;
             open_row();
         }
     }
 
-    // src/bitbuffer.c:22-56
+    // src/bitbuffer.c:22-56; bit i of a row lives in byte i/8 at (7 - i%8): within a
+    // little-endian word that is shift (i & 31) ^ 7
     R4_HD void add_bit(int bit)
     {
         first_row();
         if (bits == 65535u) return;
-        if (bits > 0 && (bits % (kBbCols * 8)) == 0) { // spill into the next physical row
+        if (bits > 0 && (bits & (kBbCols * 8 - 1)) == 0) { // spill into the next physical row
             if (free_row < (unsigned)kBbRows)
                 free_row++;
             else
                 return;
         }
-        acc |= (unsigned)bit << (7 - (bits & 7));
+        acc |= (uint32_t)bit << ((bits & 31) ^ 7);
         bits++;
-        if (num_rows == 1) first_row_bits = bits;
-        if ((bits & 7) == 0) flush_byte();
+        if ((bits & 31) == 0) flush_word();
     }
 
     // src/bitbuffer.c:106-122
@@ -164,22 +162,20 @@ struct EventWriter {
     {
         first_row();
         if (free_row < (unsigned)kBbRows) {
+            if (num_rows == 1) row0_bits = bits;
             close_row();
             free_row++;
             // physical rows taken by spill-over sit between the old and the new last row
             for (unsigned r = num_rows; r + 1 < free_row; ++r) {
-                put16(pos, 0);
-                put16(pos + 2, 0);
-                put16(pos + 4, 0);
-                pos += kRowHdr;
+                put(pos, 0);
+                pos += 1;
             }
             num_rows = free_row;
             open_row();
         } else {
             // row count exhausted: length forgotten, bytes (and syncs) stay
-            if (bits & 7) flush_byte();
+            if (bits & 31) flush_word();
             bits = 0;
-            if (num_rows == 1) first_row_bits = 0;
             dirty = true;
             acc = 0;
         }
@@ -193,22 +189,20 @@ struct EventWriter {
         syncs++;
     }
 
-    R4_HD unsigned last_row_bits() const { return bits; }
-
     // account_event(): hand the buffer to the decoder, then clear it (src/pulse_slicer.c:26-66)
     R4_HD void emit()
     {
-        if (num_rows == 0) { // an empty buffer is still an event (e.g. nrzs), header only
+        if (num_rows == 0) { // an empty buffer is still an event (e.g. nrzs): header only
             ev_start = pos;
-            pos += kEventHdr;
+            pos += 1;
         } else {
             close_row();
+            if (dirty) { // only the last row can be: its data length travels in a trailer word
+                put(pos, row_hw);
+                pos += 1;
+            }
         }
-        put16(ev_start, num_rows);
-        put16(ev_start + 2, free_row);
-        unsigned len = pos - ev_start;
-        put16(ev_start + 4, len & 0xffffu);
-        put16(ev_start + 6, len >> 16);
+        put(ev_start, num_rows | (dirty ? 0x80u : 0u) | (free_row << 8) | ((pos - ev_start) << 16));
         committed = pos;
         events++;
         reset_event();
@@ -306,7 +300,7 @@ R4_HD void slice_pcm(PulseView const &p, SlicerParams const &t, W &w)
             w.reset_event();
         else if (p.gap[n] > gap_limit && p.gap[n] <= t.s_reset)
             w.add_row();
-        if ((n == N - 1 || p.gap[n] > t.s_reset) && (w.first_row_bits > 0 || w.num_rows > 1)) w.emit();
+        if ((n == N - 1 || p.gap[n] > t.s_reset) && (w.first_row_bits() > 0 || w.num_rows > 1)) w.emit();
     }
 }
 
@@ -332,7 +326,7 @@ R4_HD void slice_ppm(PulseView const &p, SlicerParams const &t, W &w)
         else if (g > o_lo && g < o_hi) w.add_bit(1);
         else if (g > s_lo && g < s_hi) w.add_sync();
         else if (g < t.s_reset) w.add_row();
-        if ((n == p.n - 1 || g >= t.s_reset) && (w.first_row_bits > 0 || w.num_rows > 1)) w.emit();
+        if ((n == p.n - 1 || g >= t.s_reset) && (w.first_row_bits() > 0 || w.num_rows > 1)) w.emit();
     }
 }
 
@@ -550,7 +544,7 @@ R4_HD void slice_rzi(PulseView const &p, SlicerParams const &t, W &w)
         fresh = false;
         for (int k = 0; k < ones; ++k) w.add_bit(1);
         if (p.gap[n] > t.s_reset || n == p.n - 1) {
-            if (w.first_row_bits > 0) w.emit();
+            if (w.first_row_bits() > 0) w.emit();
             w.reset_event();
             fresh = true;
             continue;

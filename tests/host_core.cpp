@@ -79,15 +79,15 @@ void slice_package(Hc &h, int type, uint32_t rate, int const *pulse, int const *
             if (dp != prio) continue;
             if (!device_takes((int)h.devs[i].modulation, type)) continue;
             SlicerParams sp = scale_device(h.devs[i], rate);
-            EventWriter<false> cw;
+            EventWriter cw;
             cw.init(nullptr);
             slice_dispatch(pv, sp, cw);
-            std::vector<uint8_t> buf(cw.committed + 8, 0xAA);
-            EventWriter<true> sw;
+            std::vector<uint32_t> buf(cw.committed + 2, 0xAAAAAAAAu);
+            EventWriter sw;
             sw.init(buf.data(), cw.committed);
             slice_dispatch(pv, sp, sw);
-            for (unsigned g = cw.committed; g < cw.committed + 8; ++g)
-                if (buf[g] != 0xAA) {
+            for (unsigned g = cw.committed; g < cw.committed + 2; ++g)
+                if (buf[g] != 0xAAAAAAAAu) {
                     fprintf(stderr, "host_core: store pass wrote past its region (dev %zu)\n", i);
                     abort();
                 }
@@ -100,7 +100,7 @@ void slice_package(Hc &h, int type, uint32_t rate, int const *pulse, int const *
             for (unsigned e = 0; e < sw.events; ++e) {
                 bitbuffer bb;
                 uint32_t used = 0;
-                if (event_to_bitbuffer(buf.data() + at, sw.committed - at, 0, &bb, &used)) {
+                if (event_to_bitbuffer((uint8_t const *)buf.data() + at, sw.committed * 4 - at, 0, &bb, &used)) {
                     fprintf(stderr, "host_core: corrupt event stream\n");
                     abort();
                 }
