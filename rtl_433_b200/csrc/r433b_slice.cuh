@@ -2,11 +2,17 @@
 // encoder they write through.  __host__ __device__ inlines: device code in r433b_kernels.cu,
 // CPU-side unit tests through tests/host_core.cpp.
 //
-// One slicer run = one (package, device) pair, executed by one thread.  Instead of building a
-// 6604-byte bitbuffer_t (include/bitbuffer.h:34-40) per event, rows are streamed straight into
-// the pair's private output region in the wire format below; the host re-inflates a real
-// bitbuffer_t only when it calls a decoder (r433b_host.cpp).  Every run is executed twice by
-// the kernel: once counting (size), once storing.
+// One slicer run = one (package, device) pair, executed by one thread; the 32 lanes of a warp
+// are 32 devices looking at the SAME package.  To keep those lanes converged every slicer is
+// split into a small per-modulation "front end" that turns one pulse (or symbol) into a fixed
+// record of bit-buffer operations (Step: runs of ones/zeros, a row operation, a single bit, an
+// emit condition, trailing zeros -- always in that order) and ONE shared "back end" that applies
+// the record to the event writer.  Lanes of different devices then differ only in predicates.
+//
+// Instead of building a 6604-byte bitbuffer_t (include/bitbuffer.h:34-40) per event, rows are
+// streamed straight into the pair's private output region in the wire format below; the host
+// re-inflates a real bitbuffer_t only when it calls a decoder (r433b_host.hpp).  Every run is
+// executed twice by the kernel: once counting (size), once storing.
 //
 //   event   := u32 { num_rows:7, dirty:1, free_row:8, words:16 }   words = whole event incl. this
 //              row*  [u32 last_row_words  -- only if dirty]
@@ -52,8 +58,19 @@ struct SlicerParams {
 
 // ----------------------------------------------------------------------------- writer ----
 
+R4_HD uint32_t bswap32(uint32_t v)
+{
+#ifdef __CUDA_ARCH__
+    return __byte_perm(v, 0, 0x0123);
+#else
+    return (v >> 24) | ((v >> 8) & 0xff00u) | ((v << 8) & 0xff0000u) | (v << 24);
+#endif
+}
+
 // One writer type serves both passes: out == nullptr only counts.  All offsets are in 32-bit
-// words; every store is one aligned word.
+// words; every store is one aligned word.  Bits are gathered MSB-first in `acc` (bit i of the
+// row at position 31 - i%32) and byte-swapped on store, which yields bitbuffer_t's layout
+// (bit i in byte i/8 at position 7 - i%8) in little-endian memory.
 struct EventWriter {
     uint32_t *out;      // pair region, or nullptr while counting
     unsigned limit;     // words the counting pass committed: rows of a trailing, never-emitted
@@ -69,7 +86,7 @@ struct EventWriter {
     unsigned row_hdr;   // word offset of its header
     unsigned bits, syncs;
     unsigned row_hw;    // data words that hold something
-    unsigned acc;       // word being assembled
+    uint32_t acc;       // word being assembled (MSB first)
     bool dirty;         // row length was reset while its bytes stayed (50-row overflow path)
 
     R4_HD void init(uint32_t *o, unsigned region_words = 0)
@@ -114,10 +131,11 @@ struct EventWriter {
         unsigned w = (bits - 1) >> 5; // the word holding the newest bit
         unsigned at = row_hdr + 1 + w;
         if (out && at < limit) {
+            uint32_t v = bswap32(acc);
             if (w < row_hw)
-                out[at] |= acc;
+                out[at] |= v;
             else
-                out[at] = acc;
+                out[at] = v;
         }
         if (w + 1 > row_hw) row_hw = w + 1;
         acc = 0;
@@ -140,22 +158,30 @@ struct EventWriter {
         }
     }
 
-    // src/bitbuffer.c:22-56; bit i of a row lives in byte i/8 at (7 - i%8): within a
-    // little-endian word that is shift (i & 31) ^ 7
-    R4_HD void add_bit(int bit)
+    // `count` calls of bitbuffer_add_bit(bits, value), src/bitbuffer.c:22-56, a word at a time
+    R4_HD void add_bits(int value, int count)
     {
         first_row();
-        if (bits == 65535u) return;
-        if (bits > 0 && (bits & (kBbCols * 8 - 1)) == 0) { // spill into the next physical row
-            if (free_row < (unsigned)kBbRows)
-                free_row++;
-            else
-                return;
+        while (count > 0) {
+            if (bits == 65535u) return; // row length limit: further bits are dropped
+            if (bits > 0 && (bits & (kBbCols * 8 - 1)) == 0) { // spill into the next physical row
+                if (free_row < (unsigned)kBbRows)
+                    free_row++;
+                else
+                    return; // no room: this and all following bits of the run are dropped
+            }
+            unsigned p = bits & 31;
+            unsigned room = 32 - p; // never crosses a 1024-bit boundary either
+            unsigned n = (unsigned)count < room ? (unsigned)count : room;
+            if (bits + n > 65535u) n = 65535u - bits;
+            if (value) acc |= (n == 32 ? 0xffffffffu : ((1u << n) - 1u)) << (room - n);
+            bits += n;
+            count -= (int)n;
+            if ((bits & 31) == 0) flush_word();
         }
-        acc |= (uint32_t)bit << ((bits & 31) ^ 7);
-        bits++;
-        if ((bits & 31) == 0) flush_word();
     }
+
+    R4_HD void add_bit(int bit) { add_bits(bit, 1); }
 
     // src/bitbuffer.c:106-122
     R4_HD void add_row()
@@ -217,342 +243,6 @@ struct PulseView {
     unsigned n;
 };
 
-R4_HD int iabs(int v) { return v < 0 ? -v : v; }
-R4_HD bool within(int v, int nominal, int tol) { return v >= nominal - tol && v <= nominal + tol; }
-
-// src/pulse_slicer.c:68-259
-template <class W>
-R4_HD void slice_pcm(PulseView const &p, SlicerParams const &t, W &w)
-{
-    if (!t.ok || t.s_long == 0) return;
-    float f_short = t.f_short, f_long = t.f_long;
-    int const gap_limit = t.s_gap ? t.s_gap : t.s_reset;
-    int const max_zeros = gap_limit / t.s_long;
-    int tol = t.s_tol;
-    if (tol <= 0) tol = t.s_long / 4;
-    bool const rz = t.s_short != t.s_long;
-    int need = rz ? 4 : 12;
-    int preamble = 0;
-    unsigned const N = p.n;
-    if (rz) {
-        for (unsigned n = 0; n < N; ++n) { // :105-132
-            int sw = 0, lw = 0, cnt = 0;
-            while (n < N && within(p.pulse[n], t.s_short, tol) && within(p.pulse[n] + p.gap[n], t.s_long, tol)) {
-                sw += p.pulse[n];
-                lw += p.pulse[n] + p.gap[n];
-                cnt++;
-                n++;
-            }
-            if (cnt >= need) {
-                f_long = fdiv((float)cnt, (float)lw);
-                f_short = fdiv((float)cnt, (float)sw);
-                need = cnt;
-                preamble = cnt;
-            }
-        }
-        if (preamble == 0) { // :134-157
-            int sw = 0, lw = 0, cnt = 0;
-            for (unsigned n = 0; n < N; ++n) {
-                if (within(p.pulse[n], t.s_short, tol) && within(p.pulse[n] + p.gap[n], t.s_long, tol)) {
-                    sw += p.pulse[n];
-                    lw += p.pulse[n] + p.gap[n];
-                    cnt++;
-                }
-            }
-            if (cnt > 8) {
-                f_long = fdiv((float)cnt, (float)lw);
-                f_short = fdiv((float)cnt, (float)sw);
-            }
-        }
-    } else {
-        for (unsigned n = 0; n < N; ++n) { // :159-180, float product then DOUBLE +0.5
-            int wsum = 0, cnt = 0;
-            while (n < N && (int)dadd((double)fmul((float)p.pulse[n], f_short), 0.5) == 1
-                    && (int)dadd((double)fmul((float)p.gap[n], f_long), 0.5) == 1) {
-                wsum += p.pulse[n] + p.gap[n];
-                cnt += 2;
-                n++;
-            }
-            if (cnt >= need) {
-                f_short = f_long = fdiv((float)cnt, (float)wsum);
-                need = cnt;
-                preamble = cnt;
-            }
-        }
-        if (preamble == 0) { // :182-214
-            int wsum = 0, cnt = 0;
-            for (unsigned n = 0; n < N; ++n) {
-                if (within(p.pulse[n], t.s_short, tol)) { wsum += p.pulse[n]; cnt += 1; }
-                if (within(p.pulse[n], 2 * t.s_short, tol)) { wsum += p.pulse[n]; cnt += 2; }
-                if (within(p.gap[n], t.s_long, tol)) { wsum += p.gap[n]; cnt += 1; }
-                if (within(p.gap[n], 2 * t.s_long, tol)) { wsum += p.gap[n]; cnt += 2; }
-            }
-            if (cnt > 20) f_short = f_long = fdiv((float)cnt, (float)wsum);
-        }
-    }
-    for (unsigned n = 0; n < N; ++n) { // :216-257
-        int highs = (int)fadd(fmul((float)p.pulse[n], f_short), 0.5f);
-        int lows = (int)fadd(fmul((float)(p.gap[n] + t.s_short - t.s_long), f_long), 0.5f);
-        for (int i = 0; i < highs; ++i) w.add_bit(1);
-        if (lows > max_zeros) lows = max_zeros;
-        for (int i = 0; i < lows; ++i) w.add_bit(0);
-        if (rz && iabs(p.pulse[n] - t.s_short) > tol)
-            w.reset_event();
-        else if (p.gap[n] > gap_limit && p.gap[n] <= t.s_reset)
-            w.add_row();
-        if ((n == N - 1 || p.gap[n] > t.s_reset) && (w.first_row_bits() > 0 || w.num_rows > 1)) w.emit();
-    }
-}
-
-// src/pulse_slicer.c:261-337
-template <class W>
-R4_HD void slice_ppm(PulseView const &p, SlicerParams const &t, W &w)
-{
-    if (!t.ok) return;
-    int z_lo, z_hi, o_lo, o_hi, s_lo = 0, s_hi = 0;
-    if (t.s_tol > 0) {
-        z_lo = t.s_short - t.s_tol; z_hi = t.s_short + t.s_tol;
-        o_lo = t.s_long - t.s_tol;  o_hi = t.s_long + t.s_tol;
-        if (t.s_sync > 0) { s_lo = t.s_sync - t.s_tol; s_hi = t.s_sync + t.s_tol; }
-    } else {
-        z_lo = 0;
-        z_hi = (t.s_short + t.s_long) / 2 + 1;
-        o_lo = z_hi - 1;
-        o_hi = t.s_gap ? t.s_gap : t.s_reset;
-    }
-    for (unsigned n = 0; n < p.n; ++n) {
-        int g = p.gap[n];
-        if (g > z_lo && g < z_hi) w.add_bit(0);
-        else if (g > o_lo && g < o_hi) w.add_bit(1);
-        else if (g > s_lo && g < s_hi) w.add_sync();
-        else if (g < t.s_reset) w.add_row();
-        if ((n == p.n - 1 || g >= t.s_reset) && (w.first_row_bits() > 0 || w.num_rows > 1)) w.emit();
-    }
-}
-
-// src/pulse_slicer.c:339-449
-template <class W>
-R4_HD void slice_pwm(PulseView const &p, SlicerParams const &t, W &w)
-{
-    if (!t.ok) return;
-    int const big = 0x7fffffff;
-    int o_lo, o_hi, z_lo, z_hi, s_lo = 0, s_hi = 0;
-    if (t.s_tol > 0) {
-        o_lo = t.s_short - t.s_tol; o_hi = t.s_short + t.s_tol;
-        z_lo = t.s_long - t.s_tol;  z_hi = t.s_long + t.s_tol;
-        if (t.s_sync > 0) { s_lo = t.s_sync - t.s_tol; s_hi = t.s_sync + t.s_tol; }
-    } else if (t.s_sync <= 0) {
-        o_lo = 0; o_hi = (t.s_short + t.s_long) / 2 + 1;
-        z_lo = o_hi - 1; z_hi = big;
-    } else if (t.s_sync < t.s_short) {
-        s_lo = 0; s_hi = (t.s_sync + t.s_short) / 2 + 1;
-        o_lo = s_hi - 1; o_hi = (t.s_short + t.s_long) / 2 + 1;
-        z_lo = o_hi - 1; z_hi = big;
-    } else if (t.s_sync < t.s_long) {
-        o_lo = 0; o_hi = (t.s_short + t.s_sync) / 2 + 1;
-        s_lo = o_hi - 1; s_hi = (t.s_sync + t.s_long) / 2 + 1;
-        z_lo = s_hi - 1; z_hi = big;
-    } else {
-        o_lo = 0; o_hi = (t.s_short + t.s_long) / 2 + 1;
-        z_lo = o_hi - 1; z_hi = (t.s_long + t.s_sync) / 2 + 1;
-        s_lo = z_hi - 1; s_hi = big;
-    }
-    for (unsigned n = 0; n < p.n; ++n) {
-        int v = p.pulse[n];
-        if (v > o_lo && v < o_hi) w.add_bit(1);
-        else if (v > z_lo && v < z_hi) w.add_bit(0);
-        else if (v > s_lo && v < s_hi) w.add_sync();
-        else if (v <= o_lo) { }
-        else w.add_row();
-        if ((n == p.n - 1 || p.gap[n] > t.s_reset) && w.num_rows > 0)
-            w.emit();
-        else if (t.s_gap > 0 && p.gap[n] > t.s_gap && w.num_rows > 0 && w.last_row_bits() > 0)
-            w.add_row();
-    }
-}
-
-// src/pulse_slicer.c:451-527; the 1.5 x short comparisons are in double
-template <class W>
-R4_HD void slice_manchester(PulseView const &p, SlicerParams const &t, W &w)
-{
-    if (!t.ok) return;
-    int since = 0;
-    w.add_bit(0);
-    double const edge = dmul((double)t.s_short, 1.5);
-    int const lo = t.s_short - t.s_tol, hi = t.s_short * 2 + t.s_tol;
-    for (unsigned n = 0; n < p.n; ++n) {
-        int v = p.pulse[n], g = p.gap[n];
-        if (t.s_tol > 0 && (v < lo || v > hi || g < lo || g > hi)) {
-            if ((double)v > edge && v <= hi) w.add_bit(1);
-            w.add_row();
-            w.add_bit(0);
-            since = 0;
-        } else if ((double)(v + since) > edge) {
-            w.add_bit(1);
-            since = 0;
-        } else {
-            since += v;
-        }
-        if ((n == p.n - 1 || g > t.s_reset) && w.num_rows > 0) {
-            w.emit();
-            w.add_bit(0);
-            since = 0;
-        } else if ((double)(g + since) > edge) {
-            w.add_bit(0);
-            since = 0;
-        } else {
-            since += g;
-        }
-    }
-}
-
-R4_HD int symbol_at(PulseView const &p, unsigned k) { return (k & 1) ? p.gap[k >> 1] : p.pulse[k >> 1]; } // :529-535
-
-// src/pulse_slicer.c:537-595
-template <class W>
-R4_HD void slice_dmc(PulseView const &p, SlicerParams const &t, W &w)
-{
-    if (!t.ok) return;
-    unsigned const total = p.n * 2;
-    for (unsigned k = 0; k < total; ++k) {
-        int s = symbol_at(p, k);
-        if (iabs(s - t.s_short) < t.s_tol) {
-            w.add_bit(1);
-            s = k + 1 < total ? symbol_at(p, ++k) : 0;
-            if (iabs(s - t.s_short) > t.s_tol) {
-                if (s >= t.s_reset - t.s_tol)
-                    k--;
-                else if (w.num_rows > 0 && w.last_row_bits() > 0)
-                    w.add_row();
-            }
-        } else if (iabs(s - t.s_long) < t.s_tol) {
-            w.add_bit(0);
-        } else if (s >= t.s_reset - t.s_tol && w.num_rows > 0) {
-            w.emit();
-        }
-    }
-}
-
-// src/pulse_slicer.c:597-657
-template <class W>
-R4_HD void slice_piwm_raw(PulseView const &p, SlicerParams const &t, W &w)
-{
-    if (!t.ok) return;
-    unsigned const total = p.n * 2;
-    for (unsigned k = 0; k < total; ++k) {
-        int s = symbol_at(p, k);
-        int cnt = (int)dadd((double)fmul((float)s, t.f_short), 0.5);
-        if (s > t.s_long) {
-            w.add_row();
-        } else if (iabs(s - cnt * t.s_short) < t.s_tol) {
-            for (; cnt > 0; --cnt) w.add_bit(1 - (int)(k & 1));
-        } else if (s < t.s_reset && w.num_rows > 0 && w.last_row_bits() > 0) {
-            w.add_row();
-        }
-        if ((k == total - 1 || s > t.s_reset) && w.num_rows > 0) w.emit();
-    }
-}
-
-// src/pulse_slicer.c:659-713
-template <class W>
-R4_HD void slice_piwm_dc(PulseView const &p, SlicerParams const &t, W &w)
-{
-    if (!t.ok) return;
-    unsigned const total = p.n * 2;
-    for (unsigned k = 0; k < total; ++k) {
-        int s = symbol_at(p, k);
-        if (iabs(s - t.s_short) < t.s_tol) w.add_bit(1);
-        else if (iabs(s - t.s_long) < t.s_tol) w.add_bit(0);
-        else if (s < t.s_reset && w.num_rows > 0 && w.last_row_bits() > 0) w.add_row();
-        if ((k == total - 1 || s > t.s_reset) && w.num_rows > 0) w.emit();
-    }
-}
-
-// src/pulse_slicer.c:715-759
-template <class W>
-R4_HD void slice_nrzs(PulseView const &p, SlicerParams const &t, W &w)
-{
-    if (!t.ok || t.s_short == 0) return;
-    int const limit = t.s_short;
-    for (unsigned n = 0; n < p.n; ++n) {
-        if (p.pulse[n] > limit) {
-            int reps = p.pulse[n] / limit;
-            for (int i = 0; i < reps; ++i) w.add_bit(1);
-            w.add_bit(0);
-        } else if (p.pulse[n] < limit) {
-            w.add_bit(0);
-        }
-        if (n == p.n - 1 || p.gap[n] >= t.s_reset) w.emit();
-    }
-}
-
-// src/pulse_slicer.c:775-864
-template <class W>
-R4_HD void slice_osv1(PulseView const &p, SlicerParams const &t, W &w)
-{
-    if (!t.ok) return;
-    int pre = 0, man = 0;
-    int const half_lo = t.s_short / 2, half_hi = t.s_short * 3 / 2, sync_lo = 2 * half_hi;
-    unsigned n;
-    for (n = 0; n < p.n; ++n) {
-        if (p.pulse[n] > half_lo && p.gap[n] > half_lo) {
-            pre++;
-            if (p.gap[n] > half_hi) break;
-        } else {
-            return;
-        }
-    }
-    if (pre != 12) return;
-    ++n;
-    if (n >= (unsigned)kMaxPulses) return; // the reference reads past the array here
-    // n may equal num_pulses: the entry after the last pulse is part of the package record
-    if (p.pulse[n] < sync_lo || p.gap[n] < sync_lo) return;
-    if (p.gap[n] > p.pulse[n]) {
-        man ^= 1;
-        if (man) w.add_bit(0);
-    }
-    for (n++; n < p.n; ++n) {
-        man ^= 1;
-        if (man) w.add_bit(1);
-        if (p.pulse[n] > half_hi) {
-            man ^= 1;
-            if (man) w.add_bit(1);
-        }
-        if ((n == p.n - 1 || p.gap[n] > t.s_reset) && w.num_rows > 0) {
-            w.emit();
-            return;
-        }
-        man ^= 1;
-        if (man) w.add_bit(0);
-        if (p.gap[n] > half_hi) {
-            man ^= 1;
-            if (man) w.add_bit(0);
-        }
-    }
-}
-
-// src/pulse_slicer.c:866-918 (its rate check only looks at short/long/reset: `ok` bit 1)
-template <class W>
-R4_HD void slice_rzi(PulseView const &p, SlicerParams const &t, W &w)
-{
-    if (!(t.ok & 2) || t.s_long == 0) return;
-    int const s_base = t.s_long - t.s_short;
-    bool fresh = true;
-    for (unsigned n = 0; n < p.n; ++n) {
-        int high = p.pulse[n];
-        int ones = fresh ? (high + t.s_long / 2) / t.s_long : (high - s_base + t.s_long / 2) / t.s_long;
-        fresh = false;
-        for (int k = 0; k < ones; ++k) w.add_bit(1);
-        if (p.gap[n] > t.s_reset || n == p.n - 1) {
-            if (w.first_row_bits() > 0) w.emit();
-            w.reset_event();
-            fresh = true;
-            continue;
-        }
-        w.add_bit(0);
-    }
-}
-
 enum { // include/r_device.h:24-40
     kModOokMc = 3, kModOokPcm = 4, kModOokPpm = 5, kModOokPwm = 6, kModOokPiwmRaw = 8, kModOokDmc = 9,
     kModOokOsv1 = 10, kModOokPiwmDc = 11, kModOokNrzs = 12, kModOokRzi = 13,
@@ -566,21 +256,438 @@ R4_HD bool device_takes(int modulation, int package_type)
     return modulation >= 16 && modulation <= 18;
 }
 
+R4_HD int iabs(int v) { return v < 0 ? -v : v; }
+R4_HD bool within(int v, int nominal, int tol) { return v >= nominal - tol && v <= nominal + tol; }
+R4_HD int symbol_at(PulseView const &p, unsigned k) { return (k & 1) ? p.gap[k >> 1] : p.pulse[k >> 1]; } // src/pulse_slicer.c:529-535
+
+// What one iteration of a slicer's main loop does to the bit buffer, in this fixed order.
+enum { kRowNone = 0, kRowAdd, kRowSync, kRowClear, kRowIfOpen };
+enum { kEmitNone = 0, kEmitAlways, kEmitIfRows, kEmitIfData, kEmitIfRow0, kEmitElseRowIfOpen };
+struct Step {
+    int ones;       // 1. run of one-bits
+    int zeros;      // 2. run of zero-bits
+    int row;        // 3. kRow*: add_row / add_sync / clear / add_row if the last row has bits
+    int bit;        // 4. single bit: 0 none, 1 -> add_bit(0), 2 -> add_bit(1)
+    int emit;       // 5. kEmit*: condition under which the event is handed over
+    bool stop_if_emitted, clear_after;
+    int post_zeros; // 6. zero-bits after a (non-stopping) emit decision
+};
+
+// Per-run state of the front ends (a union in spirit: each slicer uses a few fields)
+struct SlicerState {
+    unsigned k, total;     // loop index / bound (pulses, or symbols for the PIWM/DMC family)
+    int b0, b1, b2, b3, b4, b5; // PWM / PPM class bounds
+    float f_short, f_long; // PCM tuned reciprocals
+    int i0, i1, i2;        // gap_limit / max_zeros / tol (PCM); lo / hi (MC); half_hi (OSV1); s_base (RZI)
+    int since;             // MC: time since last edge; OSV1: manchester phase; RZI: fresh flag
+    double edge;           // MC: 1.5 * s_short
+    bool pending;          // OSV1: a zero bit owed before the first data pulse
+};
+
+// ---- set-up: everything the reference does before its main loop; returns false if the slicer
+//      produces nothing (src/pulse_slicer.c, "check for rounding to zero" and early returns)
+R4_HD bool slicer_begin(PulseView const &p, SlicerParams const &t, SlicerState &st)
+{
+    st.k = 0;
+    st.total = p.n;
+    st.since = 0;
+    st.pending = false;
+    int const big = 0x7fffffff;
+    switch (t.modulation) {
+    case kModOokPwm: case kModFskPwm: { // src/pulse_slicer.c:369-413; b0..b5 = one/zero/sync lo,hi
+        if (!t.ok) return false;
+        st.b4 = st.b5 = 0;
+        if (t.s_tol > 0) {
+            st.b0 = t.s_short - t.s_tol; st.b1 = t.s_short + t.s_tol;
+            st.b2 = t.s_long - t.s_tol;  st.b3 = t.s_long + t.s_tol;
+            if (t.s_sync > 0) { st.b4 = t.s_sync - t.s_tol; st.b5 = t.s_sync + t.s_tol; }
+        } else if (t.s_sync <= 0) {
+            st.b0 = 0; st.b1 = (t.s_short + t.s_long) / 2 + 1;
+            st.b2 = st.b1 - 1; st.b3 = big;
+        } else if (t.s_sync < t.s_short) {
+            st.b4 = 0; st.b5 = (t.s_sync + t.s_short) / 2 + 1;
+            st.b0 = st.b5 - 1; st.b1 = (t.s_short + t.s_long) / 2 + 1;
+            st.b2 = st.b1 - 1; st.b3 = big;
+        } else if (t.s_sync < t.s_long) {
+            st.b0 = 0; st.b1 = (t.s_short + t.s_sync) / 2 + 1;
+            st.b4 = st.b1 - 1; st.b5 = (t.s_sync + t.s_long) / 2 + 1;
+            st.b2 = st.b5 - 1; st.b3 = big;
+        } else {
+            st.b0 = 0; st.b1 = (t.s_short + t.s_long) / 2 + 1;
+            st.b2 = st.b1 - 1; st.b3 = (t.s_long + t.s_sync) / 2 + 1;
+            st.b4 = st.b3 - 1; st.b5 = big;
+        }
+        return true;
+    }
+    case kModOokPpm: { // :291-308; b0..b5 = zero/one/sync lo,hi
+        if (!t.ok) return false;
+        st.b4 = st.b5 = 0;
+        if (t.s_tol > 0) {
+            st.b0 = t.s_short - t.s_tol; st.b1 = t.s_short + t.s_tol;
+            st.b2 = t.s_long - t.s_tol;  st.b3 = t.s_long + t.s_tol;
+            if (t.s_sync > 0) { st.b4 = t.s_sync - t.s_tol; st.b5 = t.s_sync + t.s_tol; }
+        } else {
+            st.b0 = 0;
+            st.b1 = (t.s_short + t.s_long) / 2 + 1;
+            st.b2 = st.b1 - 1;
+            st.b3 = t.s_gap ? t.s_gap : t.s_reset;
+        }
+        return true;
+    }
+    case kModOokPcm: case kModFskPcm: { // :89-214, the bit-period estimators
+        if (!t.ok || t.s_long == 0) return false;
+        float f_short = t.f_short, f_long = t.f_long;
+        int const gap_limit = t.s_gap ? t.s_gap : t.s_reset;
+        int tol = t.s_tol;
+        if (tol <= 0) tol = t.s_long / 4;
+        bool const rz = t.s_short != t.s_long;
+        int need = rz ? 4 : 12;
+        int preamble = 0;
+        unsigned const N = p.n;
+        if (rz) {
+            for (unsigned n = 0; n < N; ++n) { // :105-132
+                int sw = 0, lw = 0, cnt = 0;
+                while (n < N && within(p.pulse[n], t.s_short, tol) && within(p.pulse[n] + p.gap[n], t.s_long, tol)) {
+                    sw += p.pulse[n];
+                    lw += p.pulse[n] + p.gap[n];
+                    cnt++;
+                    n++;
+                }
+                if (cnt >= need) {
+                    f_long = fdiv((float)cnt, (float)lw);
+                    f_short = fdiv((float)cnt, (float)sw);
+                    need = cnt;
+                    preamble = cnt;
+                }
+            }
+            if (preamble == 0) { // :134-157
+                int sw = 0, lw = 0, cnt = 0;
+                for (unsigned n = 0; n < N; ++n) {
+                    if (within(p.pulse[n], t.s_short, tol) && within(p.pulse[n] + p.gap[n], t.s_long, tol)) {
+                        sw += p.pulse[n];
+                        lw += p.pulse[n] + p.gap[n];
+                        cnt++;
+                    }
+                }
+                if (cnt > 8) {
+                    f_long = fdiv((float)cnt, (float)lw);
+                    f_short = fdiv((float)cnt, (float)sw);
+                }
+            }
+        } else {
+            for (unsigned n = 0; n < N; ++n) { // :159-180, float product then DOUBLE +0.5
+                int wsum = 0, cnt = 0;
+                while (n < N && (int)dadd((double)fmul((float)p.pulse[n], f_short), 0.5) == 1
+                        && (int)dadd((double)fmul((float)p.gap[n], f_long), 0.5) == 1) {
+                    wsum += p.pulse[n] + p.gap[n];
+                    cnt += 2;
+                    n++;
+                }
+                if (cnt >= need) {
+                    f_short = f_long = fdiv((float)cnt, (float)wsum);
+                    need = cnt;
+                    preamble = cnt;
+                }
+            }
+            if (preamble == 0) { // :182-214
+                int wsum = 0, cnt = 0;
+                for (unsigned n = 0; n < N; ++n) {
+                    if (within(p.pulse[n], t.s_short, tol)) { wsum += p.pulse[n]; cnt += 1; }
+                    if (within(p.pulse[n], 2 * t.s_short, tol)) { wsum += p.pulse[n]; cnt += 2; }
+                    if (within(p.gap[n], t.s_long, tol)) { wsum += p.gap[n]; cnt += 1; }
+                    if (within(p.gap[n], 2 * t.s_long, tol)) { wsum += p.gap[n]; cnt += 2; }
+                }
+                if (cnt > 20) f_short = f_long = fdiv((float)cnt, (float)wsum);
+            }
+        }
+        st.f_short = f_short;
+        st.f_long = f_long;
+        st.i0 = gap_limit;
+        st.i1 = gap_limit / t.s_long; // max_zeros
+        st.i2 = tol;
+        return true;
+    }
+    case kModOokMc: case kModFskMc: // :451-478
+        if (!t.ok) return false;
+        st.edge = dmul((double)t.s_short, 1.5);
+        st.i0 = t.s_short - t.s_tol;
+        st.i1 = t.s_short * 2 + t.s_tol;
+        st.pending = true; // "First rising edge is always counted as a zero"
+        return true;
+    case kModOokDmc: case kModOokPiwmRaw: case kModOokPiwmDc:
+        if (!t.ok) return false;
+        st.total = p.n * 2;
+        return true;
+    case kModOokNrzs:
+        return t.ok && t.s_short != 0;
+    case kModOokOsv1: { // :797-835: twelve preamble pulses, a sync, then manchester data
+        if (!t.ok) return false;
+        int const half_lo = t.s_short / 2, half_hi = t.s_short * 3 / 2, sync_lo = 2 * half_hi;
+        int pre = 0;
+        unsigned n;
+        for (n = 0; n < p.n; ++n) {
+            if (p.pulse[n] > half_lo && p.gap[n] > half_lo) {
+                pre++;
+                if (p.gap[n] > half_hi) break;
+            } else {
+                return false;
+            }
+        }
+        if (pre != 12) return false;
+        ++n;
+        if (n >= (unsigned)kMaxPulses) return false; // the reference reads past the array here
+        // n may equal num_pulses: the entry after the last pulse is part of the package record
+        if (p.pulse[n] < sync_lo || p.gap[n] < sync_lo) return false;
+        st.since = 0; // manchester phase
+        if (p.gap[n] > p.pulse[n]) {
+            st.since = 1;
+            st.pending = true;
+        }
+        st.k = n + 1;
+        st.i0 = half_hi;
+        return true;
+    }
+    case kModOokRzi: // :866-885 (its rate check only looks at short/long/reset: `ok` bit 1)
+        if (!(t.ok & 2) || t.s_long == 0) return false;
+        st.i0 = t.s_long - t.s_short;
+        st.since = 1; // at_start
+        return true;
+    default:
+        return false;
+    }
+}
+
+// ---- one iteration of the main loop of the slicer -> what it does to the bit buffer
+R4_HD Step slicer_step(PulseView const &p, SlicerParams const &t, SlicerState &st)
+{
+    Step s;
+    s.ones = s.zeros = s.post_zeros = 0;
+    s.row = kRowNone;
+    s.bit = 0;
+    s.emit = kEmitNone;
+    s.stop_if_emitted = s.clear_after = false;
+    unsigned const n = st.k;
+    switch (t.modulation) {
+    case kModOokPwm: case kModFskPwm: { // src/pulse_slicer.c:415-447
+        int v = p.pulse[n], g = p.gap[n];
+        if (v > st.b0 && v < st.b1) s.ones = 1;
+        else if (v > st.b2 && v < st.b3) s.zeros = 1;
+        else if (v > st.b4 && v < st.b5) s.row = kRowSync;
+        else if (v <= st.b0) { }
+        else s.row = kRowAdd;
+        if (n == st.total - 1 || g > t.s_reset) s.emit = kEmitIfRows;
+        else if (t.s_gap > 0 && g > t.s_gap) s.emit = kEmitElseRowIfOpen;
+        st.k = n + 1;
+        break;
+    }
+    case kModOokPpm: { // :310-335
+        int g = p.gap[n];
+        if (g > st.b0 && g < st.b1) s.zeros = 1;
+        else if (g > st.b2 && g < st.b3) s.ones = 1;
+        else if (g > st.b4 && g < st.b5) s.row = kRowSync;
+        else if (g < t.s_reset) s.row = kRowAdd;
+        if (n == st.total - 1 || g >= t.s_reset) s.emit = kEmitIfData;
+        st.k = n + 1;
+        break;
+    }
+    case kModOokPcm: case kModFskPcm: { // :216-257
+        int v = p.pulse[n], g = p.gap[n];
+        int highs = (int)fadd(fmul((float)v, st.f_short), 0.5f);
+        int lows = (int)fadd(fmul((float)(g + t.s_short - t.s_long), st.f_long), 0.5f);
+        if (lows > st.i1) lows = st.i1;
+        s.ones = highs > 0 ? highs : 0;
+        s.zeros = lows > 0 ? lows : 0;
+        if (t.s_short != t.s_long && iabs(v - t.s_short) > st.i2) s.row = kRowClear;
+        else if (g > st.i0 && g <= t.s_reset) s.row = kRowAdd;
+        if (n == st.total - 1 || g > t.s_reset) s.emit = kEmitIfData;
+        st.k = n + 1;
+        break;
+    }
+    case kModOokMc: case kModFskMc: { // :478-525; the buffer always holds >= 1 row here
+        if (st.pending) { // bitbuffer_add_bit(&bits, 0) in front of the loop
+            st.pending = false;
+            s.zeros = 1;
+            break;
+        }
+        int v = p.pulse[n], g = p.gap[n];
+        int const lo = st.i0, hi = st.i1;
+        if (t.s_tol > 0 && (v < lo || v > hi || g < lo || g > hi)) {
+            if ((double)v > st.edge && v <= hi) s.ones = 1;
+            s.row = kRowAdd;
+            s.bit = 1;
+            st.since = 0;
+        } else if ((double)(v + st.since) > st.edge) {
+            s.ones = 1;
+            st.since = 0;
+        } else {
+            st.since += v;
+        }
+        if (n == st.total - 1 || g > t.s_reset) {
+            s.emit = kEmitIfRows;
+            s.post_zeros = 1;
+            st.since = 0;
+        } else if ((double)(g + st.since) > st.edge) {
+            s.post_zeros = 1;
+            st.since = 0;
+        } else {
+            st.since += g;
+        }
+        st.k = n + 1;
+        break;
+    }
+    case kModOokDmc: { // :562-592 (consumes a second symbol after a short one)
+        unsigned k = n;
+        int sym = symbol_at(p, k);
+        if (iabs(sym - t.s_short) < t.s_tol) {
+            s.ones = 1;
+            sym = k + 1 < st.total ? symbol_at(p, ++k) : 0;
+            if (iabs(sym - t.s_short) > t.s_tol) {
+                if (sym >= t.s_reset - t.s_tol)
+                    k--;
+                else
+                    s.row = kRowIfOpen;
+            }
+        } else if (iabs(sym - t.s_long) < t.s_tol) {
+            s.zeros = 1;
+        } else if (sym >= t.s_reset - t.s_tol) {
+            s.emit = kEmitIfRows;
+        }
+        st.k = k + 1;
+        break;
+    }
+    case kModOokPiwmRaw: { // :627-654
+        int sym = symbol_at(p, n);
+        int cnt = (int)dadd((double)fmul((float)sym, t.f_short), 0.5);
+        if (sym > t.s_long) {
+            s.row = kRowAdd;
+        } else if (iabs(sym - cnt * t.s_short) < t.s_tol) {
+            if (cnt > 0) {
+                if (n & 1) s.zeros = cnt; else s.ones = cnt;
+            }
+        } else if (sym < t.s_reset) {
+            s.row = kRowIfOpen;
+        }
+        if (n == st.total - 1 || sym > t.s_reset) s.emit = kEmitIfRows;
+        st.k = n + 1;
+        break;
+    }
+    case kModOokPiwmDc: { // :684-710
+        int sym = symbol_at(p, n);
+        if (iabs(sym - t.s_short) < t.s_tol) s.ones = 1;
+        else if (iabs(sym - t.s_long) < t.s_tol) s.zeros = 1;
+        else if (sym < t.s_reset) s.row = kRowIfOpen;
+        if (n == st.total - 1 || sym > t.s_reset) s.emit = kEmitIfRows;
+        st.k = n + 1;
+        break;
+    }
+    case kModOokNrzs: { // :741-756
+        int v = p.pulse[n];
+        if (v > t.s_short) {
+            s.ones = v / t.s_short;
+            s.zeros = 1;
+        } else if (v < t.s_short) {
+            s.zeros = 1;
+        }
+        if (n == st.total - 1 || p.gap[n] >= t.s_reset) s.emit = kEmitAlways;
+        st.k = n + 1;
+        break;
+    }
+    case kModOokOsv1: { // :837-862
+        if (st.pending) { // a data bit hidden in the sync gap
+            st.pending = false;
+            s.zeros = 1;
+            break;
+        }
+        int man = st.since;
+        man ^= 1;
+        if (man) s.ones++;
+        if (p.pulse[n] > st.i0) {
+            man ^= 1;
+            if (man) s.ones++;
+        }
+        if (n == st.total - 1 || p.gap[n] > t.s_reset) {
+            s.emit = kEmitIfRows;
+            s.stop_if_emitted = true;
+        }
+        man ^= 1;
+        if (man) s.post_zeros++;
+        if (p.gap[n] > st.i0) {
+            man ^= 1;
+            if (man) s.post_zeros++;
+        }
+        st.since = man;
+        st.k = n + 1;
+        break;
+    }
+    case kModOokRzi: { // :887-915
+        int high = p.pulse[n];
+        int ones = st.since ? (high + t.s_long / 2) / t.s_long : (high - st.i0 + t.s_long / 2) / t.s_long;
+        st.since = 0;
+        s.ones = ones > 0 ? ones : 0;
+        if (p.gap[n] > t.s_reset || n == st.total - 1) {
+            s.emit = kEmitIfRow0;
+            s.clear_after = true;
+            st.since = 1;
+        } else {
+            s.post_zeros = 1;
+        }
+        st.k = n + 1;
+        break;
+    }
+    default:
+        st.k = st.total;
+        break;
+    }
+    return s;
+}
+
+// ---- the shared back end.  Returns false when the slicer is finished (OSV1 after its event).
+template <class W>
+R4_HD bool slicer_apply(Step const &s, W &w)
+{
+    if (s.ones) w.add_bits(1, s.ones);
+    if (s.zeros) w.add_bits(0, s.zeros);
+    if (s.row != kRowNone) {
+        if (s.row == kRowAdd)
+            w.add_row();
+        else if (s.row == kRowSync)
+            w.add_sync();
+        else if (s.row == kRowClear)
+            w.reset_event();
+        else if (w.num_rows > 0 && w.last_row_bits() > 0)
+            w.add_row();
+    }
+    if (s.bit) w.add_bits(s.bit - 1, 1);
+    bool emitted = false;
+    if (s.emit != kEmitNone) {
+        bool go;
+        if (s.emit == kEmitAlways) go = true;
+        else if (s.emit == kEmitIfRows) go = w.num_rows > 0;
+        else if (s.emit == kEmitIfData) go = w.first_row_bits() > 0 || w.num_rows > 1;
+        else if (s.emit == kEmitIfRow0) go = w.first_row_bits() > 0;
+        else {
+            go = false;
+            if (w.num_rows > 0 && w.last_row_bits() > 0) w.add_row();
+        }
+        if (go) {
+            w.emit();
+            emitted = true;
+        }
+    }
+    if (s.clear_after) w.reset_event();
+    if (emitted && s.stop_if_emitted) return false;
+    if (s.post_zeros) w.add_bits(0, s.post_zeros);
+    return true;
+}
+
 template <class W>
 R4_HD void slice_dispatch(PulseView const &p, SlicerParams const &t, W &w)
 {
-    switch (t.modulation) {
-    case kModOokPcm: case kModFskPcm: slice_pcm(p, t, w); break;
-    case kModOokPpm: slice_ppm(p, t, w); break;
-    case kModOokPwm: case kModFskPwm: slice_pwm(p, t, w); break;
-    case kModOokMc: case kModFskMc: slice_manchester(p, t, w); break;
-    case kModOokPiwmRaw: slice_piwm_raw(p, t, w); break;
-    case kModOokPiwmDc: slice_piwm_dc(p, t, w); break;
-    case kModOokDmc: slice_dmc(p, t, w); break;
-    case kModOokOsv1: slice_osv1(p, t, w); break;
-    case kModOokNrzs: slice_nrzs(p, t, w); break;
-    case kModOokRzi: slice_rzi(p, t, w); break;
-    default: break;
+    SlicerState st;
+    if (!slicer_begin(p, t, st)) return;
+    while (st.k < st.total || st.pending) {
+        Step s = slicer_step(p, t, st);
+        if (!slicer_apply(s, w)) break;
     }
 }
 
