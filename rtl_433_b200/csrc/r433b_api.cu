@@ -295,10 +295,16 @@ int r433b_process(r433b_ctx *ctx, r433b_batch const *b)
             unsigned grid = (b->n_streams + kDetectWarps - 1) / kDetectWarps;
             if (SS == 2) {
                 size_t sm = (size_t)kDetectWarps * TileCfg<2>::kTileWords * sizeof(uint32_t);
-                k_detect<2><<<grid, kDetectWarps * 32, sm, st>>>(dp);
+                if (dp.wrap_free)
+                    k_detect<2, true><<<grid, kDetectWarps * 32, sm, st>>>(dp);
+                else
+                    k_detect<2, false><<<grid, kDetectWarps * 32, sm, st>>>(dp);
             } else {
                 size_t sm = (size_t)kDetectWarps * TileCfg<4>::kTileWords * sizeof(uint32_t);
-                k_detect<4><<<grid, kDetectWarps * 32, sm, st>>>(dp);
+                if (dp.wrap_free)
+                    k_detect<4, true><<<grid, kDetectWarps * 32, sm, st>>>(dp);
+                else
+                    k_detect<4, false><<<grid, kDetectWarps * 32, sm, st>>>(dp);
             }
             CU(cudaGetLastError());
             detect_launches++;

@@ -51,6 +51,25 @@ R4_HD int mag_cs16(int i, int q)
     return (int)(((122u * hi + 51u * lo) >> 8) & 0xffffu);
 }
 
+// t / den with C semantics (truncation toward zero) for |t| < 2^30, 1 <= den <= 2^17 and
+// |t / den| < 2^14.  On the device: float reciprocal estimate (error < 0.01 in the quotient)
+// plus one exact integer correction step, instead of the generic 32-bit division sequence.
+R4_HD int div_trunc_small(int t, int den)
+{
+#ifdef __CUDA_ARCH__
+    unsigned u = (unsigned)(t < 0 ? -t : t);
+    int q = (int)(__fmul_rn((float)u, __frcp_rn((float)den)));
+    int r = (int)u - q * den;
+    if (r < 0)
+        q -= 1;
+    else if (r >= den)
+        q += 1;
+    return t < 0 ? -q : q;
+#else
+    return t / den;
+#endif
+}
+
 // src/baseband.c:181-202: pi == 32767, truncating division, (0,0) -> 0
 R4_HD int atan16(int y, int x)
 {
@@ -66,8 +85,8 @@ R4_HD int atan16(int y, int x)
         num = x + ay;
         base = 24575;
     }
-    // den >= 1 here: it is 0 only for x == y == 0
-    int ang = base - 8191 * num / den;
+    // den >= 1 here: it is 0 only for x == y == 0; |num| <= den <= 65536
+    int ang = base - div_trunc_small(8191 * num, den);
     return (int)(int16_t)(y < 0 ? -ang : ang);
 }
 
@@ -94,6 +113,13 @@ R4_HD int atan32(int y, int x)
 R4_HD int iir16(int y, int a1, int b0, int xsum)
 {
     return (int)(int16_t)((a1 * y + b0 * xsum) >> 14);
+}
+
+// the same step when the host has proved the state can never leave the int16 range
+// (coefficients non-negative with a1 + 2*b0 <= 16384): the int16 store is then the identity
+R4_HD int iir16_nowrap(int y, int a1, int b0, int xsum)
+{
+    return (a1 * y + b0 * xsum) >> 14;
 }
 
 // the Q0.30 variant of the cs16 FM filter, int64 accumulate (src/baseband.c:357)

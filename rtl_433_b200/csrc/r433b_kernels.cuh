@@ -30,6 +30,7 @@ namespace r433b {
 
 constexpr int kTrainInts = 4 * kMaxPulses; // per-stream scratch: ook pulse/gap, fsk pulse/gap
 constexpr int kDetectWarps = 4;            // warps (streams) per CTA
+constexpr int kDetectCtasPerSm = 7;        // 28 warps per SM: 4096 streams are co-resident on 148 SMs
 
 struct DetectParams {
     uint8_t const *data;
@@ -76,8 +77,8 @@ struct TileCfg {
     static constexpr int kTileWords = 32 * (W * C + 1);
 };
 
-template <int SS>
-__global__ void __launch_bounds__(kDetectWarps * 32) k_detect(DetectParams p)
+template <int SS, bool NOWRAP>
+__global__ void __launch_bounds__(kDetectWarps * 32, kDetectCtasPerSm) k_detect(DetectParams p)
 {
     using Cfg = TileCfg<SS>;
     constexpr int C = Cfg::C;
@@ -267,6 +268,7 @@ __global__ void __launch_bounds__(kDetectWarps * 32) k_detect(DetectParams p)
         }
         int const a1 = p.lpf_a1, b0 = p.lpf_b0;
         long long const fa1 = p.fm_a1, fb0 = p.fm_b0;
+        auto step16 = [](int y, int ca, int cb, int xsum) { return NOWRAP ? iir16_nowrap(y, ca, cb, xsum) : iir16(y, ca, cb, xsum); };
 
         // both ends of both brackets advance together: four independent dependency chains
         auto run_chunk2 = [&](int &ya0, int &ya1, int &yf0, int &yf1) {
@@ -276,15 +278,15 @@ __global__ void __launch_bounds__(kDetectWarps * 32) k_detect(DetectParams p)
                 uint32_t w0 = mine[k * W];
                 int x = (int)(w0 & 0xffff);
                 int xsum = x + xp;
-                ya0 = iir16(ya0, a1, b0, xsum);
-                ya1 = iir16(ya1, a1, b0, xsum);
+                ya0 = step16(ya0, a1, b0, xsum);
+                ya1 = step16(ya1, a1, b0, xsum);
                 xp = x;
                 if (fm_on) {
                     if (SS == 2) {
                         int v = (int)(int16_t)(w0 >> 16);
                         int fsum = v + fp;
-                        yf0 = iir16(yf0, (int)fa1, (int)fb0, fsum);
-                        yf1 = iir16(yf1, (int)fa1, (int)fb0, fsum);
+                        yf0 = step16(yf0, (int)fa1, (int)fb0, fsum);
+                        yf1 = step16(yf1, (int)fa1, (int)fb0, fsum);
                         fp = v;
                     } else {
                         int v = (int)mine[k * W + 1];
@@ -311,7 +313,7 @@ __global__ void __launch_bounds__(kDetectWarps * 32) k_detect(DetectParams p)
         for (int round = 0; round < 31; ++round) {
             bool mine_ok = (lo_a == hi_a) && (!fm_on || lo_f == hi_f);
             // lanes 0..round are exact by induction even if the filter could wrap
-            bool trust = p.wrap_free ? mine_ok : (lane <= round);
+            bool trust = NOWRAP ? mine_ok : (lane <= round);
             if (__all_sync(0xffffffffu, trust)) break;
             int ea_lo = lo_a, ea_hi = hi_a, ef_lo = lo_f, ef_hi = hi_f;
             run_chunk2(ea_lo, ea_hi, ef_lo, ef_hi);
@@ -336,13 +338,13 @@ __global__ void __launch_bounds__(kDetectWarps * 32) k_detect(DetectParams p)
             for (int k = 0; k < nv; ++k) {
                 uint32_t w0 = mine[k * W];
                 int x = (int)(w0 & 0xffff);
-                ya = iir16(ya, a1, b0, x + xp);
+                ya = step16(ya, a1, b0, x + xp);
                 xp = x;
                 int fo;
                 if (fm_on) {
                     if (SS == 2) {
                         int v = (int)(int16_t)(w0 >> 16);
-                        yf = iir16(yf, (int)fa1, (int)fb0, v + fp);
+                        yf = step16(yf, (int)fa1, (int)fb0, v + fp);
                         fp = v;
                         fo = yf;
                     } else {
@@ -400,10 +402,18 @@ __global__ void __launch_bounds__(kDetectWarps * 32) k_detect(DetectParams p)
             if (cnt == 0) return 0;
             int q = d.low;
             int b = a + lane;
-#pragma unroll 8
-            for (int j = 0; j < cnt; ++j) {
-                int bj = __shfl_sync(0xffffffffu, b, j);
-                if (bj > q) q += 2;
+            if (cnt == 32) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    int bj = __shfl_sync(0xffffffffu, b, j);
+                    if (bj > q) q += 2;
+                }
+            } else {
+#pragma unroll 4
+                for (int j = 0; j < cnt; ++j) {
+                    int bj = __shfl_sync(0xffffffffu, b, j);
+                    if (bj > q) q += 2;
+                }
             }
             d.low = q - cnt;
             int hh = p.lv.ratio * d.low;
