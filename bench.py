@@ -50,8 +50,8 @@ def _gen_one(args):
     return synth.fsk_stream(seed, n_samples=n).view(np.uint8)
 
 
-def generate(kind, distinct, n, seed0=0):
-    jobs = [(kind, seed0 + s, n) for s in range(distinct)]
+def generate(kind, seeds, n):
+    jobs = [(kind, s, n) for s in seeds]
     procs = min(len(jobs), max(1, (os.cpu_count() or 2) // 2), 32)
     if procs > 1:
         with mp.get_context("spawn").Pool(procs) as pool:
@@ -204,8 +204,12 @@ def run_gpu(a, w):
     streams = a.streams or w["streams"]
     distinct = min(a.distinct, streams)
     # file i of the whole job goes to rank i mod world (round-robin shard, BASELINE configs[3]);
-    # with seeded synthetic files that is simply a different seed range per rank
-    base = generate(w["kind"], distinct, n, seed0=rank * distinct)
+    # file i carries the synthetic capture with seed i mod (distinct * world)
+    from rtl_433_b200 import shard
+    my_files = shard.files_for_rank(streams * world, rank, world)
+    seeds = sorted({f % (distinct * world) for f in my_files})
+    base_by_seed = dict(zip(seeds, generate(w["kind"], seeds, n)))
+    base = [base_by_seed[f % (distinct * world)] for f in my_files[:distinct]]
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -221,6 +225,7 @@ def run_gpu(a, w):
     devs = lib.default_device_table()
     ctx = lib.Context(local)
     ctx.set_devices(devs)
+    ctx.set_pipeline(a.pipeline)
 
     def barrier():
         if world > 1:
@@ -333,6 +338,7 @@ def main():
     ap.add_argument("--ref-streams-per-core", type=int, default=192,
                     help="stream passes per host core in the reference/cpu_baseline leg (~22 ms each)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--pipeline", type=int, default=0, help="host-input pipeline groups (0 auto, 1 off)")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 0)
     w = WORKLOADS[a.workload]

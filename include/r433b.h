@@ -106,7 +106,7 @@ typedef struct r433b_results {
 
 /* Wall/device timing of the last r433b_process(), milliseconds. */
 typedef struct r433b_timing {
-    float h2d_ms, detect_ms, slice_ms, d2h_ms, total_ms;
+    float h2d_ms, detect_ms, slice_ms, d2h_ms, total_ms; /* pipelined batches: kernel sums + wall total only */
     uint32_t detect_launches, slice_launches;
 } r433b_timing;
 
@@ -118,6 +118,10 @@ char const *r433b_last_error(r433b_ctx const *ctx);
 int r433b_set_levels(r433b_ctx *ctx, int use_mag_est, float level_limit_db, float min_level_db, float min_snr_db);
 /* -Y filter / dm_state.fm_low_pass; 0 = automatic (src/r_flow.c:204) */
 int r433b_set_fm_low_pass(r433b_ctx *ctx, float fm_low_pass);
+
+/* Host-input batches are cut into `groups` runs of streams whose copy-in, kernels and copy-out
+   overlap (0 = automatic, 1 = no overlap, <= 16).  Results are identical either way. */
+int r433b_set_pipeline(r433b_ctx *ctx, int groups);
 
 /* The registered decoder list in registration order (cfg->demod->r_devs, src/r_api.c:267). */
 int r433b_set_devices(r433b_ctx *ctx, r433b_device const *devs, uint32_t n);

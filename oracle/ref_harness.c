@@ -608,3 +608,33 @@ REFH_EXPORT int refh_slice_all(refh_t *h, int fsk, uint32_t sample_rate, uint32_
     g_active = NULL;
     return (int)h->n_evts;
 }
+
+/* Hand the registered r_device structs to an EXTERNAL dispatcher (the product's
+   r433b_dispatch_r_devices): real decode_fn restored, output collected by this harness. */
+REFH_EXPORT r_device **refh_begin_external_dispatch(refh_t *h)
+{
+    clear_results(h);
+    for (int i = 0; i < h->n_devs; ++i) {
+        r_device *d = h->devs[i];
+        d->decode_fn = h->orig_fn[i];
+        d->decode_events = d->decode_ok = d->decode_messages = 0;
+        memset(d->decode_fails, 0, sizeof(d->decode_fails));
+    }
+    g_active = h;
+    return h->devs;
+}
+
+REFH_EXPORT void refh_end_external_dispatch(refh_t *h)
+{
+    for (int i = 0; i < h->n_devs; ++i) h->devs[i]->decode_fn = capture_cb;
+    g_active = NULL;
+}
+
+REFH_EXPORT void refh_reset_stats(refh_t *h)
+{
+    for (int i = 0; i < h->n_devs; ++i) {
+        r_device *d = h->devs[i];
+        d->decode_events = d->decode_ok = d->decode_messages = 0;
+        memset(d->decode_fails, 0, sizeof(d->decode_fails));
+    }
+}

@@ -99,6 +99,10 @@ def lib():
         L.refh_abi_facts.argtypes = [C.POINTER(C.c_uint32)]
         L.refh_slice.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]
         L.refh_slice_all.argtypes = [C.c_void_p, C.c_int, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]
+        L.refh_begin_external_dispatch.restype = C.c_void_p
+        L.refh_begin_external_dispatch.argtypes = [C.c_void_p]
+        L.refh_end_external_dispatch.argtypes = [C.c_void_p]
+        L.refh_reset_stats.argtypes = [C.c_void_p]
         L.refh_envelope_detect.restype = C.c_float
         L.refh_envelope_detect.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
         L.refh_magnitude_est_cu8.restype = C.c_float

@@ -5,6 +5,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <chrono>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -61,6 +62,14 @@ struct r433b_ctx {
     HostBuf h_pkgs, h_ppool, h_gpool, h_pairs, h_events, h_small;
     r433b_timing timing{};
     cudaEvent_t ev[6]{};
+    // pipelined path (host input): copy-in / detect / slice / copy-out streams and per-group events
+    int pipeline_groups = 0; // 0 = automatic, 1 = off
+    cudaStream_t s_in = nullptr, s_det = nullptr, s_slc = nullptr, s_out = nullptr;
+    static constexpr int kMaxGroups = 16;
+    cudaEvent_t ev_in[kMaxGroups]{}, ev_det[kMaxGroups]{}, ev_slc[kMaxGroups]{}, ev_t[4 * kMaxGroups]{}, ev_init = nullptr;
+    DevBuf d_ranges, d_state;
+    HostBuf h_ranges;
+    bool d2h_done = false;
 };
 
 namespace {
@@ -132,6 +141,15 @@ int r433b_create(int cuda_device, r433b_ctx **out)
         return R433B_ECUDA;
     }
     for (auto &v : ctx->ev) cudaEventCreate(&v);
+    cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking);
+    cudaStreamCreateWithFlags(&ctx->s_det, cudaStreamNonBlocking);
+    cudaStreamCreateWithFlags(&ctx->s_slc, cudaStreamNonBlocking);
+    cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking);
+    for (auto &v : ctx->ev_in) cudaEventCreateWithFlags(&v, cudaEventDisableTiming);
+    for (auto &v : ctx->ev_det) cudaEventCreateWithFlags(&v, cudaEventDisableTiming);
+    for (auto &v : ctx->ev_slc) cudaEventCreateWithFlags(&v, cudaEventDisableTiming);
+    for (auto &v : ctx->ev_t) cudaEventCreate(&v);
+    cudaEventCreateWithFlags(&ctx->ev_init, cudaEventDisableTiming);
     ctx->lv = compute_levels(0, 0.0f, -12.1442f, 9.0f);
     *out = ctx;
     return R433B_OK;
@@ -143,12 +161,21 @@ void r433b_destroy(r433b_ctx *ctx)
     cudaSetDevice(ctx->device);
     for (DevBuf *b : {&ctx->d_data, &ctx->d_offsets, &ctx->d_train, &ctx->d_pkgs, &ctx->d_ppool, &ctx->d_gpool,
                  &ctx->d_counters, &ctx->d_am, &ctx->d_fm, &ctx->d_devparams, &ctx->d_lists, &ctx->d_pairs,
-                 &ctx->d_arena, &ctx->d_cursor})
+                 &ctx->d_arena, &ctx->d_cursor, &ctx->d_ranges, &ctx->d_state})
         if (b->p) cudaFree(b->p);
-    for (HostBuf *b : {&ctx->h_pkgs, &ctx->h_ppool, &ctx->h_gpool, &ctx->h_pairs, &ctx->h_events, &ctx->h_small})
+    for (HostBuf *b : {&ctx->h_pkgs, &ctx->h_ppool, &ctx->h_gpool, &ctx->h_pairs, &ctx->h_events, &ctx->h_small,
+                 &ctx->h_ranges})
         if (b->p) cudaFreeHost(b->p);
     for (auto &v : ctx->ev)
         if (v) cudaEventDestroy(v);
+    for (auto *arr : {ctx->ev_in, ctx->ev_det, ctx->ev_slc})
+        for (int i = 0; i < r433b_ctx::kMaxGroups; ++i)
+            if (arr[i]) cudaEventDestroy(arr[i]);
+    for (auto &v : ctx->ev_t)
+        if (v) cudaEventDestroy(v);
+    if (ctx->ev_init) cudaEventDestroy(ctx->ev_init);
+    for (cudaStream_t st : {ctx->s_in, ctx->s_det, ctx->s_slc, ctx->s_out})
+        if (st) cudaStreamDestroy(st);
     delete ctx;
 }
 
@@ -169,6 +196,13 @@ int r433b_set_fm_low_pass(r433b_ctx *ctx, float v)
 {
     if (!ctx) return R433B_EINVAL;
     ctx->fm_low_pass = v;
+    return R433B_OK;
+}
+
+int r433b_set_pipeline(r433b_ctx *ctx, int groups)
+{
+    if (!ctx || groups < 0 || groups > r433b_ctx::kMaxGroups) return R433B_EINVAL;
+    ctx->pipeline_groups = groups;
     return R433B_OK;
 }
 
@@ -228,24 +262,21 @@ int r433b_process(r433b_ctx *ctx, r433b_batch const *b)
         if (d.modulation >= 16) ctx->enable_fm = 1;
 
     cudaStream_t const st = 0;
-    CU(cudaEventRecord(ctx->ev[0], st));
+    ctx->d2h_done = false;
 
-    // ---- inputs ---------------------------------------------------------------------
+    // ---- device buffers and launch parameters (no data moved yet) -----------------------
     uint8_t const *d_in;
     if (b->data_on_device) {
         d_in = (uint8_t const *)b->data;
     } else {
         if (int r = dev_reserve(ctx, ctx->d_data, total_bytes + 64)) return r;
-        if (total_bytes) CU(cudaMemcpyAsync(ctx->d_data.p, b->data, total_bytes, cudaMemcpyHostToDevice, st));
         d_in = (uint8_t const *)ctx->d_data.p;
     }
     if (int r = dev_reserve(ctx, ctx->d_offsets, (b->n_streams + 1) * sizeof(uint64_t))) return r;
-    CU(cudaMemcpyAsync(ctx->d_offsets.p, ctx->offsets.data(), (b->n_streams + 1) * sizeof(uint64_t),
-            cudaMemcpyHostToDevice, st));
-    CU(cudaEventRecord(ctx->ev[1], st));
-
+    CU(cudaMemcpy(ctx->d_offsets.p, ctx->offsets.data(), (b->n_streams + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice));
     if (int r = dev_reserve(ctx, ctx->d_train, (size_t)std::max(1u, b->n_streams) * kTrainInts * sizeof(int))) return r;
     if (int r = dev_reserve(ctx, ctx->d_counters, 64)) return r;
+    if (int r = dev_reserve(ctx, ctx->d_cursor, 64)) return r;
     if (b->want_stages) {
         if (int r = dev_reserve(ctx, ctx->d_am, total_bytes / SS * sizeof(int16_t) + 16)) return r;
         if (int r = dev_reserve(ctx, ctx->d_fm, total_bytes / SS * sizeof(int16_t) + 16)) return r;
@@ -255,6 +286,12 @@ int r433b_process(r433b_ctx *ctx, r433b_batch const *b)
     dp.data = d_in;
     dp.offsets = (unsigned long long const *)ctx->d_offsets.p;
     dp.n_streams = b->n_streams;
+    dp.stream0 = 0;
+    dp.stream_end = b->n_streams;
+    dp.sample_begin = 0;
+    dp.sample_end = ~0ull;
+    dp.first_chunk = 1;
+    dp.state = nullptr;
     dp.use_mag = ctx->use_mag;
     dp.enable_fm = ctx->enable_fm;
     dp.fpdm = (int)ctx->fpdm;
@@ -276,52 +313,26 @@ int r433b_process(r433b_ctx *ctx, r433b_batch const *b)
     dp.am_out = b->want_stages ? (int16_t *)ctx->d_am.p : nullptr;
     dp.fm_out = b->want_stages ? (int16_t *)ctx->d_fm.p : nullptr;
 
-    if (ctx->pkg_cap < (size_t)b->n_streams * 16 + 1024) ctx->pkg_cap = (size_t)b->n_streams * 16 + 1024;
-    if (ctx->pool_cap < ctx->pkg_cap * 128) ctx->pool_cap = ctx->pkg_cap * 128;
-
-    unsigned detect_launches = 0;
-    unsigned counters[4] = {0, 0, 0, 0};
-    for (int attempt = 0; attempt < 3; ++attempt) {
-        if (int r = dev_reserve(ctx, ctx->d_pkgs, ctx->pkg_cap * sizeof(r433b_package))) return r;
-        if (int r = dev_reserve(ctx, ctx->d_ppool, ctx->pool_cap * sizeof(int))) return r;
-        if (int r = dev_reserve(ctx, ctx->d_gpool, ctx->pool_cap * sizeof(int))) return r;
-        dp.pkgs = (r433b_package *)ctx->d_pkgs.p;
-        dp.pkg_cap = (unsigned)std::min<size_t>(ctx->pkg_cap, 0xffffffffu);
-        dp.pulse_pool = (int *)ctx->d_ppool.p;
-        dp.gap_pool = (int *)ctx->d_gpool.p;
-        dp.pool_cap = (unsigned)std::min<size_t>(ctx->pool_cap, 0xffffffffu);
-        CU(cudaMemsetAsync(ctx->d_counters.p, 0, 64, st));
-        if (b->n_streams) {
-            unsigned grid = (b->n_streams + kDetectWarps - 1) / kDetectWarps;
-            if (SS == 2) {
-                size_t sm = (size_t)kDetectWarps * TileCfg<2>::kTileWords * sizeof(uint32_t);
-                if (dp.wrap_free)
-                    k_detect<2, true><<<grid, kDetectWarps * 32, sm, st>>>(dp);
-                else
-                    k_detect<2, false><<<grid, kDetectWarps * 32, sm, st>>>(dp);
-            } else {
-                size_t sm = (size_t)kDetectWarps * TileCfg<4>::kTileWords * sizeof(uint32_t);
-                if (dp.wrap_free)
-                    k_detect<4, true><<<grid, kDetectWarps * 32, sm, st>>>(dp);
-                else
-                    k_detect<4, false><<<grid, kDetectWarps * 32, sm, st>>>(dp);
-            }
-            CU(cudaGetLastError());
-            detect_launches++;
+    auto launch_detect = [&](DetectParams const &q, cudaStream_t s) {
+        unsigned n = q.stream_end - q.stream0;
+        if (!n) return;
+        unsigned grid = (n + kDetectWarps - 1) / kDetectWarps;
+        if (SS == 2) {
+            size_t sm = (size_t)kDetectWarps * TileCfg<2>::kTileWords * sizeof(uint32_t);
+            if (q.wrap_free)
+                k_detect<2, true><<<grid, kDetectWarps * 32, sm, s>>>(q);
+            else
+                k_detect<2, false><<<grid, kDetectWarps * 32, sm, s>>>(q);
+        } else {
+            size_t sm = (size_t)kDetectWarps * TileCfg<4>::kTileWords * sizeof(uint32_t);
+            if (q.wrap_free)
+                k_detect<4, true><<<grid, kDetectWarps * 32, sm, s>>>(q);
+            else
+                k_detect<4, false><<<grid, kDetectWarps * 32, sm, s>>>(q);
         }
-        CU(cudaMemcpyAsync(counters, ctx->d_counters.p, sizeof(counters), cudaMemcpyDeviceToHost, st));
-        CU(cudaStreamSynchronize(st));
-        if (!counters[2]) break;
-        // arenas were too small: the counters hold the true need
-        ctx->pkg_cap = std::max<size_t>(ctx->pkg_cap, (size_t)counters[0] + 64);
-        ctx->pool_cap = std::max<size_t>(ctx->pool_cap, (size_t)counters[1] + 4096);
-        if (attempt == 2) return fail(ctx, R433B_EOVERFLOW, "package arena overflow");
-    }
-    ctx->n_pkgs = counters[0];
-    ctx->pool_used = counters[1];
-    CU(cudaEventRecord(ctx->ev[2], st));
+    };
 
-    // ---- slicers ----------------------------------------------------------------------
+    // slicer parameters: per device, scaled to this batch's sample rate on the host
     std::vector<SlicerParams> sp(n_devs);
     std::vector<unsigned> ook, fsk;
     for (uint32_t i = 0; i < n_devs; ++i) sp[i] = scale_device(ctx->devs[i], b->samp_rate);
@@ -341,41 +352,227 @@ int r433b_process(r433b_ctx *ctx, r433b_batch const *b)
     std::sort(fsk.begin(), fsk.end(), by_mod);
     ctx->n_ook = (unsigned)ook.size();
     ctx->n_fsk = (unsigned)fsk.size();
+    if (int r = dev_reserve(ctx, ctx->d_devparams, std::max<size_t>(1, n_devs) * sizeof(SlicerParams))) return r;
+    if (int r = dev_reserve(ctx, ctx->d_lists, (ook.size() + fsk.size() + 1) * sizeof(unsigned))) return r;
+    if (n_devs) CU(cudaMemcpy(ctx->d_devparams.p, sp.data(), n_devs * sizeof(SlicerParams), cudaMemcpyHostToDevice));
+    if (!ook.empty()) CU(cudaMemcpy(ctx->d_lists.p, ook.data(), ook.size() * sizeof(unsigned), cudaMemcpyHostToDevice));
+    if (!fsk.empty())
+        CU(cudaMemcpy((unsigned *)ctx->d_lists.p + ook.size(), fsk.data(), fsk.size() * sizeof(unsigned), cudaMemcpyHostToDevice));
+
+    if (ctx->pkg_cap < (size_t)b->n_streams * 16 + 1024) ctx->pkg_cap = (size_t)b->n_streams * 16 + 1024;
+    if (ctx->pool_cap < ctx->pkg_cap * 128) ctx->pool_cap = ctx->pkg_cap * 128;
+    if (ctx->arena_cap < total_bytes / 2 + (1u << 20)) ctx->arena_cap = total_bytes / 2 + (1u << 20);
+
+    auto fill_slice = [&](SliceParams &q) {
+        q.pkgs = (r433b_package *)ctx->d_pkgs.p;
+        q.range = nullptr;
+        q.pulse_pool = (int const *)ctx->d_ppool.p;
+        q.gap_pool = (int const *)ctx->d_gpool.p;
+        q.dev = (SlicerParams const *)ctx->d_devparams.p;
+        q.n_devs = n_devs;
+        q.ook_list = (unsigned const *)ctx->d_lists.p;
+        q.fsk_list = (unsigned const *)ctx->d_lists.p + ook.size();
+        q.n_ook = ctx->n_ook;
+        q.n_fsk = ctx->n_fsk;
+        q.pairs = (r433b_pair *)ctx->d_pairs.p;
+        q.arena = (uint8_t *)ctx->d_arena.p;
+        q.arena_cap = ctx->arena_cap;
+        q.cursor = (unsigned long long *)ctx->d_cursor.p;
+    };
+
+    // ---- pipelined path: host input cut into G TIME SLICES of every stream; copy-in of slice
+    //      k+1, detect of slice k, slicing of the packages slice k-1 completed and copy-out overlap
+    //      on four streams.  (Cutting by streams instead does not help: a warp needs the same
+    //      wall time for its stream however few other warps run.)  Detector / filter state is
+    //      carried between launches in `StreamState`; results are identical to one launch. ----
+    int G = ctx->pipeline_groups;
+    uint64_t stride = b->n_streams ? ctx->offsets[1] - ctx->offsets[0] : 0;
+    bool uniform = b->n_streams > 0 && stride > 0;
+    for (uint32_t i = 0; uniform && i < b->n_streams; ++i)
+        if (ctx->offsets[i + 1] - ctx->offsets[i] != stride) uniform = false;
+    if (G == 0) // measured on B200: 8 slices of >= 256 KiB per stream beat fewer, larger ones
+        G = (total_bytes >= (256ull << 20) && stride >= (1u << 20)) ? (int)std::min<uint64_t>(8, stride / (256u << 10)) : 1;
+    if (b->data_on_device || b->want_stages || !n_devs || !uniform) G = 1;
+    uint64_t slice_samples = 0;
+    if (G > 1) {
+        uint64_t n_samp = stride / SS;
+        uint64_t unit = std::max<uint64_t>((uint64_t)T, dp.block_samples); // keep slices block aligned
+        slice_samples = (n_samp / G + unit - 1) / unit * unit;
+        if (slice_samples == 0 || slice_samples >= n_samp) G = 1;
+        else G = (int)((n_samp + slice_samples - 1) / slice_samples);
+        if (G > r433b_ctx::kMaxGroups) G = 1;
+    }
+    if (G > 1) {
+        using clk = std::chrono::steady_clock;
+        auto t_wall0 = clk::now();
+        if (int r = dev_reserve(ctx, ctx->d_pkgs, ctx->pkg_cap * sizeof(r433b_package))) return r;
+        if (int r = dev_reserve(ctx, ctx->d_ppool, ctx->pool_cap * sizeof(int))) return r;
+        if (int r = dev_reserve(ctx, ctx->d_gpool, ctx->pool_cap * sizeof(int))) return r;
+        size_t const pair_cap_bytes = ctx->pkg_cap * n_devs * sizeof(r433b_pair);
+        if (int r = dev_reserve(ctx, ctx->d_pairs, pair_cap_bytes)) return r;
+        if (int r = dev_reserve(ctx, ctx->d_arena, ctx->arena_cap)) return r;
+        if (int r = dev_reserve(ctx, ctx->d_ranges, G * sizeof(GroupRange))) return r;
+        if (int r = dev_reserve(ctx, ctx->d_state, (size_t)b->n_streams * sizeof(StreamState))) return r;
+        if (int r = host_reserve(ctx, ctx->h_ranges, G * sizeof(GroupRange))) return r;
+        dp.pkgs = (r433b_package *)ctx->d_pkgs.p;
+        dp.pkg_cap = (unsigned)std::min<size_t>(ctx->pkg_cap, 0xffffffffu);
+        dp.pulse_pool = (int *)ctx->d_ppool.p;
+        dp.gap_pool = (int *)ctx->d_gpool.p;
+        dp.pool_cap = (unsigned)std::min<size_t>(ctx->pool_cap, 0xffffffffu);
+        dp.state = (StreamState *)ctx->d_state.p;
+        SliceParams q{};
+        fill_slice(q);
+        q.n_pkgs = dp.pkg_cap;
+        GroupRange *d_rg = (GroupRange *)ctx->d_ranges.p;
+        GroupRange *h_rg = (GroupRange *)ctx->h_ranges.p;
+        unsigned const *d_cnt = (unsigned const *)ctx->d_counters.p;
+        unsigned long long const *d_cur = (unsigned long long const *)ctx->d_cursor.p;
+
+        CU(cudaMemsetAsync(ctx->d_counters.p, 0, 64, ctx->s_det));
+        CU(cudaMemsetAsync(ctx->d_cursor.p, 0, 64, ctx->s_det));
+        CU(cudaMemsetAsync(ctx->d_pairs.p, 0, pair_cap_bytes, ctx->s_det));
+        CU(cudaEventRecord(ctx->ev_init, ctx->s_det));
+        CU(cudaStreamWaitEvent(ctx->s_slc, ctx->ev_init, 0));
+        for (int g = 0; g < G; ++g) {
+            uint64_t c0 = (uint64_t)g * slice_samples * SS, c1 = std::min<uint64_t>(stride, c0 + slice_samples * SS);
+            // one strided copy: the same byte range of every stream
+            CU(cudaMemcpy2DAsync((uint8_t *)ctx->d_data.p + ctx->offsets[0] + c0, stride,
+                    (uint8_t const *)b->data + ctx->offsets[0] + c0, stride, c1 - c0, b->n_streams,
+                    cudaMemcpyHostToDevice, ctx->s_in));
+            CU(cudaEventRecord(ctx->ev_in[g], ctx->s_in));
+            CU(cudaStreamWaitEvent(ctx->s_det, ctx->ev_in[g], 0));
+            k_mark<<<1, 1, 0, ctx->s_det>>>(d_rg + g, 0, d_cnt, d_cur);
+            CU(cudaEventRecord(ctx->ev_t[4 * g + 0], ctx->s_det));
+            DetectParams dg = dp;
+            dg.sample_begin = (uint64_t)g * slice_samples;
+            dg.sample_end = g == G - 1 ? ~0ull : (uint64_t)(g + 1) * slice_samples;
+            dg.first_chunk = g == 0;
+            launch_detect(dg, ctx->s_det);
+            CU(cudaEventRecord(ctx->ev_t[4 * g + 1], ctx->s_det));
+            k_mark<<<1, 1, 0, ctx->s_det>>>(d_rg + g, 1, d_cnt, d_cur);
+            CU(cudaEventRecord(ctx->ev_det[g], ctx->s_det));
+            CU(cudaStreamWaitEvent(ctx->s_slc, ctx->ev_det[g], 0));
+            k_mark<<<1, 1, 0, ctx->s_slc>>>(d_rg + g, 2, d_cnt, d_cur);
+            CU(cudaEventRecord(ctx->ev_t[4 * g + 2], ctx->s_slc));
+            SliceParams qg = q;
+            qg.range = d_rg + g;
+            k_slice<<<148 * 8, kSliceThreads, 0, ctx->s_slc>>>(qg);
+            CU(cudaEventRecord(ctx->ev_t[4 * g + 3], ctx->s_slc));
+            k_mark<<<1, 1, 0, ctx->s_slc>>>(d_rg + g, 3, d_cnt, d_cur);
+            CU(cudaMemcpyAsync(h_rg + g, d_rg + g, sizeof(GroupRange), cudaMemcpyDeviceToHost, ctx->s_slc));
+            CU(cudaEventRecord(ctx->ev_slc[g], ctx->s_slc));
+        }
+        CU(cudaGetLastError());
+        // copy-out of finished groups while later ones compute; only into host buffers that are
+        // already large enough (they are after the first batch of a given shape)
+        bool overflow = false, d2h_ok = true;
+        for (int g = 0; g < G; ++g) {
+            CU(cudaEventSynchronize(ctx->ev_slc[g]));
+            GroupRange const r = h_rg[g];
+            if (r.overflow) overflow = true;
+            if (overflow) continue;
+            size_t pk_hi = (size_t)r.pkg_end * sizeof(r433b_package), pool_hi = (size_t)r.pool_end * sizeof(int);
+            size_t pair_hi = (size_t)r.pkg_end * n_devs * sizeof(r433b_pair);
+            if (ctx->h_pkgs.cap < pk_hi || ctx->h_ppool.cap < pool_hi || ctx->h_gpool.cap < pool_hi || ctx->h_pairs.cap < pair_hi
+                    || ctx->h_events.cap < r.arena_end)
+                d2h_ok = false;
+            if (!d2h_ok) continue;
+            size_t pk_lo = (size_t)r.pkg_begin * sizeof(r433b_package), pool_lo = (size_t)r.pool_begin * sizeof(int);
+            size_t pair_lo = (size_t)r.pkg_begin * n_devs * sizeof(r433b_pair);
+            cudaStream_t so = ctx->s_out;
+            if (pk_hi > pk_lo) CU(cudaMemcpyAsync((char *)ctx->h_pkgs.p + pk_lo, (char *)ctx->d_pkgs.p + pk_lo, pk_hi - pk_lo, cudaMemcpyDeviceToHost, so));
+            if (pool_hi > pool_lo) {
+                CU(cudaMemcpyAsync((char *)ctx->h_ppool.p + pool_lo, (char *)ctx->d_ppool.p + pool_lo, pool_hi - pool_lo, cudaMemcpyDeviceToHost, so));
+                CU(cudaMemcpyAsync((char *)ctx->h_gpool.p + pool_lo, (char *)ctx->d_gpool.p + pool_lo, pool_hi - pool_lo, cudaMemcpyDeviceToHost, so));
+            }
+            if (pair_hi > pair_lo) CU(cudaMemcpyAsync((char *)ctx->h_pairs.p + pair_lo, (char *)ctx->d_pairs.p + pair_lo, pair_hi - pair_lo, cudaMemcpyDeviceToHost, so));
+            if (r.arena_end > r.arena_begin)
+                CU(cudaMemcpyAsync((char *)ctx->h_events.p + r.arena_begin, (char *)ctx->d_arena.p + r.arena_begin, r.arena_end - r.arena_begin, cudaMemcpyDeviceToHost, so));
+        }
+        CU(cudaStreamSynchronize(ctx->s_out));
+        if (!overflow) {
+            GroupRange const last = h_rg[G - 1];
+            ctx->n_pkgs = last.pkg_end;
+            ctx->pool_used = last.pool_end;
+            ctx->event_bytes = last.arena_end;
+            ctx->n_events = last.events_end;
+            ctx->n_samples = total_bytes / SS;
+            ctx->d2h_done = d2h_ok;
+            float det = 0, slc = 0;
+            for (int g = 0; g < G; ++g) {
+                float a = 0, c = 0;
+                cudaEventElapsedTime(&a, ctx->ev_t[4 * g + 0], ctx->ev_t[4 * g + 1]);
+                cudaEventElapsedTime(&c, ctx->ev_t[4 * g + 2], ctx->ev_t[4 * g + 3]);
+                det += a;
+                slc += c;
+            }
+            ctx->timing.h2d_ms = 0; // overlapped: only the wall total is meaningful
+            ctx->timing.d2h_ms = 0;
+            ctx->timing.detect_ms = det;
+            ctx->timing.slice_ms = slc;
+            ctx->timing.total_ms = std::chrono::duration<float, std::milli>(clk::now() - t_wall0).count();
+            ctx->timing.detect_launches = (unsigned)G;
+            ctx->timing.slice_launches = (unsigned)G;
+            ctx->processed = true;
+            return R433B_OK;
+        }
+        // an arena was too small: grow from what the device counted and redo sequentially below
+        unsigned cnt[4];
+        unsigned long long cur[4];
+        CU(cudaMemcpy(cnt, ctx->d_counters.p, sizeof(cnt), cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy(cur, ctx->d_cursor.p, sizeof(cur), cudaMemcpyDeviceToHost));
+        ctx->pkg_cap = std::max<size_t>(ctx->pkg_cap, (size_t)cnt[0] * 2 + 64);
+        ctx->pool_cap = std::max<size_t>(ctx->pool_cap, (size_t)cnt[1] * 2 + 4096);
+        ctx->arena_cap = std::max<size_t>(ctx->arena_cap, (size_t)cur[0] * 2 + (1u << 20));
+    }
+
+    // ---- sequential path ------------------------------------------------------------------
+    CU(cudaEventRecord(ctx->ev[0], st));
+    if (!b->data_on_device && total_bytes)
+        CU(cudaMemcpyAsync(ctx->d_data.p, b->data, total_bytes, cudaMemcpyHostToDevice, st));
+    CU(cudaEventRecord(ctx->ev[1], st));
+
+    unsigned detect_launches = 0;
+    unsigned counters[4] = {0, 0, 0, 0};
+    for (int attempt = 0; attempt < 3; ++attempt) {
+        if (int r = dev_reserve(ctx, ctx->d_pkgs, ctx->pkg_cap * sizeof(r433b_package))) return r;
+        if (int r = dev_reserve(ctx, ctx->d_ppool, ctx->pool_cap * sizeof(int))) return r;
+        if (int r = dev_reserve(ctx, ctx->d_gpool, ctx->pool_cap * sizeof(int))) return r;
+        dp.pkgs = (r433b_package *)ctx->d_pkgs.p;
+        dp.pkg_cap = (unsigned)std::min<size_t>(ctx->pkg_cap, 0xffffffffu);
+        dp.pulse_pool = (int *)ctx->d_ppool.p;
+        dp.gap_pool = (int *)ctx->d_gpool.p;
+        dp.pool_cap = (unsigned)std::min<size_t>(ctx->pool_cap, 0xffffffffu);
+        CU(cudaMemsetAsync(ctx->d_counters.p, 0, 64, st));
+        if (b->n_streams) {
+            launch_detect(dp, st);
+            CU(cudaGetLastError());
+            detect_launches++;
+        }
+        CU(cudaMemcpyAsync(counters, ctx->d_counters.p, sizeof(counters), cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        if (!counters[2]) break;
+        // arenas were too small: the counters hold the true need
+        ctx->pkg_cap = std::max<size_t>(ctx->pkg_cap, (size_t)counters[0] + 64);
+        ctx->pool_cap = std::max<size_t>(ctx->pool_cap, (size_t)counters[1] + 4096);
+        if (attempt == 2) return fail(ctx, R433B_EOVERFLOW, "package arena overflow");
+    }
+    ctx->n_pkgs = counters[0];
+    ctx->pool_used = counters[1];
+    CU(cudaEventRecord(ctx->ev[2], st));
 
     unsigned long long cursor[4] = {0, 0, 0, 0};
     unsigned slice_launches = 0;
     if (ctx->n_pkgs && n_devs) {
-        if (int r = dev_reserve(ctx, ctx->d_devparams, n_devs * sizeof(SlicerParams))) return r;
-        if (int r = dev_reserve(ctx, ctx->d_lists, (ook.size() + fsk.size() + 1) * sizeof(unsigned))) return r;
-        if (int r = dev_reserve(ctx, ctx->d_cursor, 64)) return r;
-        CU(cudaMemcpyAsync(ctx->d_devparams.p, sp.data(), n_devs * sizeof(SlicerParams), cudaMemcpyHostToDevice, st));
-        if (!ook.empty())
-            CU(cudaMemcpyAsync(ctx->d_lists.p, ook.data(), ook.size() * sizeof(unsigned), cudaMemcpyHostToDevice, st));
-        if (!fsk.empty())
-            CU(cudaMemcpyAsync((unsigned *)ctx->d_lists.p + ook.size(), fsk.data(), fsk.size() * sizeof(unsigned),
-                    cudaMemcpyHostToDevice, st));
         size_t pair_bytes = (size_t)ctx->n_pkgs * n_devs * sizeof(r433b_pair);
         if (int r = dev_reserve(ctx, ctx->d_pairs, pair_bytes)) return r;
-        if (ctx->arena_cap < total_bytes / 2 + (1u << 20)) ctx->arena_cap = total_bytes / 2 + (1u << 20);
         for (int attempt = 0; attempt < 3; ++attempt) {
             if (int r = dev_reserve(ctx, ctx->d_arena, ctx->arena_cap)) return r;
             CU(cudaMemsetAsync(ctx->d_pairs.p, 0, pair_bytes, st));
             CU(cudaMemsetAsync(ctx->d_cursor.p, 0, 64, st));
             SliceParams q{};
-            q.pkgs = (r433b_package *)ctx->d_pkgs.p;
+            fill_slice(q);
             q.n_pkgs = ctx->n_pkgs;
-            q.pulse_pool = (int const *)ctx->d_ppool.p;
-            q.gap_pool = (int const *)ctx->d_gpool.p;
-            q.dev = (SlicerParams const *)ctx->d_devparams.p;
-            q.n_devs = n_devs;
-            q.ook_list = (unsigned const *)ctx->d_lists.p;
-            q.fsk_list = (unsigned const *)ctx->d_lists.p + ook.size();
-            q.n_ook = ctx->n_ook;
-            q.n_fsk = ctx->n_fsk;
-            q.pairs = (r433b_pair *)ctx->d_pairs.p;
-            q.arena = (uint8_t *)ctx->d_arena.p;
-            q.arena_cap = ctx->arena_cap;
-            q.cursor = (unsigned long long *)ctx->d_cursor.p;
             k_slice<<<ctx->n_pkgs, kSliceThreads, 0, st>>>(q);
             CU(cudaGetLastError());
             slice_launches++;
@@ -436,13 +633,16 @@ int r433b_fetch(r433b_ctx *ctx, r433b_results *out)
     if (int r = host_reserve(ctx, ctx->h_gpool, pool_bytes + 16)) return r;
     if (int r = host_reserve(ctx, ctx->h_pairs, pair_bytes + 16)) return r;
     if (int r = host_reserve(ctx, ctx->h_events, ctx->event_bytes + 16)) return r;
-    if (pk_bytes) CU(cudaMemcpyAsync(ctx->h_pkgs.p, ctx->d_pkgs.p, pk_bytes, cudaMemcpyDeviceToHost, st));
-    if (pool_bytes) {
-        CU(cudaMemcpyAsync(ctx->h_ppool.p, ctx->d_ppool.p, pool_bytes, cudaMemcpyDeviceToHost, st));
-        CU(cudaMemcpyAsync(ctx->h_gpool.p, ctx->d_gpool.p, pool_bytes, cudaMemcpyDeviceToHost, st));
+    if (!ctx->d2h_done) {
+        if (pk_bytes) CU(cudaMemcpyAsync(ctx->h_pkgs.p, ctx->d_pkgs.p, pk_bytes, cudaMemcpyDeviceToHost, st));
+        if (pool_bytes) {
+            CU(cudaMemcpyAsync(ctx->h_ppool.p, ctx->d_ppool.p, pool_bytes, cudaMemcpyDeviceToHost, st));
+            CU(cudaMemcpyAsync(ctx->h_gpool.p, ctx->d_gpool.p, pool_bytes, cudaMemcpyDeviceToHost, st));
+        }
+        if (pair_bytes && ctx->d_pairs.p) CU(cudaMemcpyAsync(ctx->h_pairs.p, ctx->d_pairs.p, pair_bytes, cudaMemcpyDeviceToHost, st));
+        if (ctx->event_bytes) CU(cudaMemcpyAsync(ctx->h_events.p, ctx->d_arena.p, ctx->event_bytes, cudaMemcpyDeviceToHost, st));
+        ctx->d2h_done = true;
     }
-    if (pair_bytes && ctx->d_pairs.p) CU(cudaMemcpyAsync(ctx->h_pairs.p, ctx->d_pairs.p, pair_bytes, cudaMemcpyDeviceToHost, st));
-    if (ctx->event_bytes) CU(cudaMemcpyAsync(ctx->h_events.p, ctx->d_arena.p, ctx->event_bytes, cudaMemcpyDeviceToHost, st));
     CU(cudaEventRecord(ctx->ev[5], st));
     CU(cudaEventSynchronize(ctx->ev[5]));
     cudaEventElapsedTime(&ctx->timing.d2h_ms, ctx->ev[4], ctx->ev[5]);

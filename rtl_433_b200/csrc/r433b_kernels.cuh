@@ -32,10 +32,23 @@ constexpr int kTrainInts = 4 * kMaxPulses; // per-stream scratch: ook pulse/gap,
 constexpr int kDetectWarps = 4;            // warps (streams) per CTA
 constexpr int kDetectCtasPerSm = 7;        // 28 warps per SM: 4096 streams are co-resident on 148 SMs
 
+// Everything one stream carries from one launch to the next when a batch is processed in
+// several time slices (so that copy-in of slice k+1 overlaps the kernels of slice k).
+struct StreamState {
+    DetState d;
+    int y_am, y_fm, x_prev, xf_prev, pr_prev, pi_prev;
+    unsigned seq;
+    int flushed;
+};
+
 struct DetectParams {
     uint8_t const *data;
     unsigned long long const *offsets; // bytes, n_streams + 1
     unsigned n_streams;
+    unsigned stream0, stream_end; // the streams this launch covers
+    unsigned long long sample_begin, sample_end; // the slice of every stream this launch covers (multiples of the tile)
+    int first_chunk;              // start from reset_sdr_flow() state instead of the saved one
+    struct StreamState *state;    // per-stream carried state between launches of one batch
     int use_mag, enable_fm, fpdm;
     unsigned rate, block_samples;
     Levels lv;
@@ -88,8 +101,8 @@ __global__ void __launch_bounds__(kDetectWarps * 32, kDetectCtasPerSm) k_detect(
 
     int const warp = threadIdx.x >> 5;
     int const lane = threadIdx.x & 31;
-    unsigned const s = blockIdx.x * kDetectWarps + warp;
-    if (s >= p.n_streams) return;
+    unsigned const s = p.stream0 + blockIdx.x * kDetectWarps + warp;
+    if (s >= p.stream_end) return;
 
     uint32_t *tile = smem + warp * Cfg::kTileWords;
     bool const fm_on = p.enable_fm != 0;
@@ -110,8 +123,6 @@ __global__ void __launch_bounds__(kDetectWarps * 32, kDetectCtasPerSm) k_detect(
     cx.nlanes = 32;
 
     DetState d;
-    det_reset(d);
-    d.ook_hw = d.fsk_hw = kMaxPulses; // scratch is not assumed to be zero: first package clears it
     unsigned seq = 0;
     int const per_ms = (int)(p.rate / 1000);
     unsigned long long const n_blocks = (N + p.block_samples - 1) / p.block_samples;
@@ -121,6 +132,23 @@ __global__ void __launch_bounds__(kDetectWarps * 32, kDetectCtasPerSm) k_detect(
     int x_prev = 0;          // raw envelope of the previous sample
     int xf_prev = 0;         // previous discriminator output
     int pr_prev = 0, pi_prev = 0; // previous IQ sample (offset removed)
+    int flushed = 0;
+    if (p.first_chunk) {
+        det_reset(d);
+        d.ook_hw = d.fsk_hw = kMaxPulses; // scratch is not assumed to be zero: first package clears it
+    } else {
+        StreamState const &ss = p.state[s];
+        d = ss.d;
+        y_am = ss.y_am;
+        y_fm = ss.y_fm;
+        x_prev = ss.x_prev;
+        xf_prev = ss.xf_prev;
+        pr_prev = ss.pr_prev;
+        pi_prev = ss.pi_prev;
+        seq = ss.seq;
+        flushed = ss.flushed;
+    }
+    unsigned long long const t_end = p.sample_end < N ? p.sample_end : N;
 
     auto emit = [&](int type, unsigned long long pos, bool flush) {
         PackageHeader h = package_header(d, type);
@@ -170,7 +198,7 @@ __global__ void __launch_bounds__(kDetectWarps * 32, kDetectCtasPerSm) k_detect(
         seq++;
     };
 
-    for (unsigned long long t0 = 0; t0 < N; t0 += T) {
+    for (unsigned long long t0 = p.sample_begin; t0 < t_end; t0 += T) {
         unsigned long long const remain = N - t0;
         int const nv_tile = remain < (unsigned long long)T ? (int)remain : T;
         int nv = nv_tile - lane * C; // valid samples in this lane's chunk
@@ -530,19 +558,63 @@ __global__ void __launch_bounds__(kDetectWarps * 32, kDetectCtasPerSm) k_detect(
         __syncwarp();
     }
 
-    // flush_sdr_flow(): len == 0 call(s) at the end of the file
-    for (;;) {
-        int ev = det_flush(d, tr, p.fpdm);
-        if (!ev) break;
-        emit(ev, N, true);
+    // flush_sdr_flow(): len == 0 call(s) at the end of the file, in the launch that reaches it
+    if (N <= p.sample_end && !flushed) {
+        for (;;) {
+            int ev = det_flush(d, tr, p.fpdm);
+            if (!ev) break;
+            emit(ev, N, true);
+        }
+        flushed = 1;
+    }
+    if (lane == 0 && p.state) {
+        StreamState &ss = p.state[s];
+        ss.d = d;
+        ss.y_am = y_am;
+        ss.y_fm = y_fm;
+        ss.x_prev = x_prev;
+        ss.xf_prev = xf_prev;
+        ss.pr_prev = pr_prev;
+        ss.pi_prev = pi_prev;
+        ss.seq = seq;
+        ss.flushed = flushed;
     }
 }
 
 // ------------------------------------------------------------------------- k_slice -------
 
+// What one pipeline group (a contiguous run of streams) produced, filled on the device so the
+// next stage never waits for the host.
+struct GroupRange {
+    unsigned pkg_begin, pkg_end;
+    unsigned pool_begin, pool_end;
+    unsigned long long arena_begin, arena_end;
+    unsigned long long events_end;
+    unsigned overflow, pad;
+};
+
+__global__ void k_mark(GroupRange *r, int which, unsigned const *counters, unsigned long long const *cursor)
+{
+    if (which == 0) {
+        r->pkg_begin = counters[0];
+        r->pool_begin = counters[1];
+    } else if (which == 1) {
+        r->pkg_end = counters[0];
+        r->pool_end = counters[1];
+        r->overflow = counters[2];
+    } else if (which == 2) {
+        r->arena_begin = cursor[0];
+    } else {
+        r->arena_end = cursor[0];
+        r->events_end = cursor[1];
+        r->overflow |= (unsigned)cursor[2] << 1;
+    }
+}
+
 struct SliceParams {
     r433b_package *pkgs;
     unsigned n_pkgs;
+    GroupRange const *range; // if set: packages [pkg_begin, min(pkg_end, n_pkgs)) instead of [0, n_pkgs)
     int const *pulse_pool, *gap_pool;
     SlicerParams const *dev;  // per device, already scaled to the batch sample rate
     unsigned n_devs;
@@ -558,8 +630,12 @@ constexpr int kSliceThreads = 128;
 
 __global__ void __launch_bounds__(kSliceThreads) k_slice(SliceParams p)
 {
-    unsigned const pk = blockIdx.x;
-    if (pk >= p.n_pkgs) return;
+    unsigned pk_begin = 0, pk_end = p.n_pkgs;
+    if (p.range) {
+        pk_begin = p.range->pkg_begin;
+        pk_end = p.range->pkg_end < p.n_pkgs ? p.range->pkg_end : p.n_pkgs;
+    }
+    for (unsigned pk = pk_begin + blockIdx.x; pk < pk_end; pk += gridDim.x) {
     r433b_package const k = p.pkgs[pk];
     unsigned const n_list = k.type == 1 ? p.n_ook : p.n_fsk;
     unsigned const *list = k.type == 1 ? p.ook_list : p.fsk_list;
@@ -623,6 +699,7 @@ __global__ void __launch_bounds__(kSliceThreads) k_slice(SliceParams p)
             p.pairs[(size_t)pk * p.n_devs + dev] = pr;
         }
     }
+    } // packages of this block
 }
 
 } // namespace r433b

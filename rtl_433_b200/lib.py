@@ -23,7 +23,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
               "-shared", "-Xcompiler", "-fPIC,-ffp-contract=off"]
 
 EXPORTS = ["r433b_create", "r433b_destroy", "r433b_last_error", "r433b_set_levels", "r433b_set_fm_low_pass",
-           "r433b_set_devices", "r433b_set_r_devices", "r433b_process", "r433b_fetch", "r433b_get_timing",
+           "r433b_set_devices", "r433b_set_r_devices", "r433b_set_pipeline", "r433b_process", "r433b_fetch", "r433b_get_timing",
            "r433b_get_counts", "r433b_copy_stage", "r433b_event_to_bitbuffer", "r433b_package_to_pulse_data",
            "r433b_package_file_pos", "r433b_dispatch", "r433b_dispatch_r_devices"]
 
@@ -117,6 +117,7 @@ def load():
     L.r433b_last_error.argtypes = [C.c_void_p]
     L.r433b_set_levels.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_float]
     L.r433b_set_fm_low_pass.argtypes = [C.c_void_p, C.c_float]
+    L.r433b_set_pipeline.argtypes = [C.c_void_p, C.c_int]
     L.r433b_set_devices.argtypes = [C.c_void_p, C.POINTER(Device), C.c_uint32]
     L.r433b_set_r_devices.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
     L.r433b_process.argtypes = [C.c_void_p, C.POINTER(Batch)]
@@ -173,6 +174,9 @@ class Context:
 
     def set_fm_low_pass(self, v):
         self._check(self.L.r433b_set_fm_low_pass(self.h, v))
+
+    def set_pipeline(self, groups):
+        self._check(self.L.r433b_set_pipeline(self.h, groups))
 
     def set_devices(self, devs):
         arr = (Device * len(devs))()

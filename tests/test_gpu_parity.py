@@ -144,3 +144,26 @@ def test_magnitude_mode_and_fixed_level(ctx, devices):
                 check(gpu[i], o.run(s, 2), f"levels {kw} {i}")
     finally:
         ctx.set_levels()
+
+
+def test_pipelined_time_slices_identical(ctx, devices):
+    """Host-input batches processed in overlapping time slices (detector and filter state carried
+    between launches) must give exactly the single-launch result."""
+    streams = [synth.ook_stream(20 + seed, n_samples=1 << 19, n_bursts=4) for seed in range(5)]
+    o = oracle_for(devices, stages=False)
+    refs = [o.run(s, 2) for s in streams]
+    lens = [s.nbytes for s in streams]
+    offsets = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
+    data = np.concatenate(streams)
+    try:
+        for groups in (3, 4, 16):
+            ctx.set_pipeline(groups)
+            ctx.process(data, offsets, lib.FMT_CU8, 250000, 433920000)
+            ctx.fetch()
+            assert ctx.timing()["detect_launches"] > 1
+            for i in range(len(streams)):
+                got = helpers.gpu_stream_results(ctx, i)
+                d = helpers.compare_results(refs[i], got, f"pipeline {groups} stream {i}", stages=False)
+                assert not d, "\n".join(d[:20])
+    finally:
+        ctx.set_pipeline(0)
