@@ -407,6 +407,122 @@ __global__ void __launch_bounds__(kDetectWarps * 32, kDetectCtasPerSm) k_detect(
         // a prefix of them, and advances the (warp-uniform) state over that prefix at once.
         // They return the number of samples consumed; 0 hands the current sample to det_step().
 
+        // IDLE over a long stretch, lane-parallel.  While |am - low| < 1024 the tracker is
+        // low += (am > low) ? +1 : -1, so low keeps the parity of (low0 + samples seen) and two
+        // trajectories of equal parity never cross and merge once the data passes between them.
+        // That is the IIR trick again: lane l takes chunk l of the tile, starts from a bracket
+        // [lo, hi] of the right parity that provably contains the true value (low can never
+        // leave [min(low0, min(am)-1), max(low0, max(am))]), pushes both ends through its chunk
+        // and hands them to the next lane until every bracket has collapsed.  Chunks in which a
+        // trigger is conceivable (or |am - low| could reach 1024) end the stretch; they are left
+        // to the 32-sample path below.
+        auto idle_tile = [&](int n) -> int {
+            if (nv_tile - n < 3 * C) return 0;
+            {
+                int hs = p.lv.ratio * d.low;
+                if (hs < p.lv.min_high) hs = p.lv.min_high;
+                if (d.high != hs) return 0;
+            }
+            int const c0 = n / C;
+            int const k0 = lane == c0 ? n - c0 * C : 0;
+            int k1 = nv_tile - lane * C;
+            k1 = k1 > C ? C : k1;
+            bool const in_region = lane >= c0 && k1 > k0;
+            uint32_t const *chunk = tile + lane * (W * C + 1);
+            int cmin = 32767, cmax = -32768;
+            if (in_region) {
+#pragma unroll 4
+                for (int k = k0; k < k1; ++k) {
+                    int a = (int)(int16_t)(chunk[k * W] & 0xffff);
+                    cmin = a < cmin ? a : cmin;
+                    cmax = a > cmax ? a : cmax;
+                }
+            }
+            int pmin = cmin, pmax = cmax; // over chunks c0..lane
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                int t1 = __shfl_up_sync(0xffffffffu, pmin, o);
+                int t2 = __shfl_up_sync(0xffffffffu, pmax, o);
+                if (lane >= o) {
+                    pmin = t1 < pmin ? t1 : pmin;
+                    pmax = t2 > pmax ? t2 : pmax;
+                }
+            }
+            int Lmin = d.low < pmin - 1 ? d.low : pmin - 1;
+            int Lmax = d.low > pmax ? d.low : pmax;
+            int hmin = p.lv.ratio * Lmin;
+            if (hmin < p.lv.min_high) hmin = p.lv.min_high;
+            Thresholds th = det_thresholds(Lmin, hmin, p.lv);
+            bool const armed = d.lead_in + (nv_tile - n) > kLeadIn;
+            bool ok = in_region && !(armed && cmax > th.up) && (pmax - Lmin < 1024) && (Lmax - pmin < 1024);
+            unsigned bad = ~__ballot_sync(0xffffffffu, ok) & (0xffffffffu << c0);
+            int const e = bad ? __ffs(bad) - 1 : 32; // chunks c0 .. e-1 form the stretch
+            if (e - c0 < 3) return 0;
+            int const RLmin = __shfl_sync(0xffffffffu, Lmin, e - 1);
+            int const RLmax = __shfl_sync(0xffffffffu, Lmax, e - 1);
+            bool const act = lane >= c0 && lane < e;
+            int const par = (d.low + (lane * C + k0 - n)) & 1; // parity of the true value at this lane's start
+            // Start bracket.  Over K samples whose values lie in [m, M] the tracker climbs one per
+            // sample until it is >= m - 1 and falls one per sample until it is <= M, so from any
+            // start in [A, B] it ends in [min(A + K, m - 1), max(B - K, M)].  Use the two chunks to
+            // the left (the one chunk and the exact start value for the second lane of the stretch).
+            int m1 = __shfl_up_sync(0xffffffffu, cmin, 1), M1 = __shfl_up_sync(0xffffffffu, cmax, 1);
+            int m2 = __shfl_up_sync(0xffffffffu, cmin, 2), M2 = __shfl_up_sync(0xffffffffu, cmax, 2);
+            int K1 = __shfl_up_sync(0xffffffffu, k1 - k0, 1);
+            int lo, hi;
+            if (lane == c0 + 1) {
+                lo = d.low + K1 < m1 - 1 ? d.low + K1 : m1 - 1;
+                hi = d.low - K1 > M1 ? d.low - K1 : M1;
+            } else {
+                int mm = m1 < m2 ? m1 : m2, MM = M1 > M2 ? M1 : M2;
+                int Kk = K1 + (lane == c0 + 2 ? 0 : C); // chunk c0 may be partial: count only lane-1 then
+                if (lane == c0 + 2) {
+                    mm = m1;
+                    MM = M1;
+                }
+                lo = RLmin + Kk < mm - 1 ? RLmin + Kk : mm - 1;
+                hi = RLmax - Kk > MM ? RLmax - Kk : MM;
+            }
+            lo = lo < RLmin ? RLmin : lo;
+            hi = hi > RLmax ? RLmax : hi;
+            lo -= (lo - par) & 1;
+            hi += (hi - par) & 1;
+            if (lane == c0) lo = hi = d.low;
+            int result = 0;
+            bool done = false;
+#pragma unroll 1
+            for (int round = 0; round < 8; ++round) {
+                int elo = lo, ehi = hi;
+                if (act) {
+#pragma unroll 4
+                    for (int k = k0; k < k1; ++k) {
+                        int a = (int)(int16_t)(chunk[k * W] & 0xffff);
+                        elo += a > elo ? 1 : -1;
+                        ehi += a > ehi ? 1 : -1;
+                    }
+                }
+                if (__all_sync(0xffffffffu, !act || elo == ehi)) {
+                    result = __shfl_sync(0xffffffffu, elo, e - 1);
+                    done = true;
+                    break;
+                }
+                int nlo = __shfl_up_sync(0xffffffffu, elo, 1);
+                int nhi = __shfl_up_sync(0xffffffffu, ehi, 1);
+                if (act && lane != c0) {
+                    lo = nlo;
+                    hi = nhi;
+                }
+            }
+            if (!done) return 0;
+            int const len = (e * C < nv_tile ? e * C : nv_tile) - n;
+            d.low = result;
+            int hh = p.lv.ratio * d.low;
+            d.high = hh < p.lv.min_high ? p.lv.min_high : hh;
+            int li = d.lead_in + len;
+            d.lead_in = li > kLeadIn + 1 ? kLeadIn + 1 : li;
+            return len;
+        };
+
         // IDLE: only the noise-floor tracker moves (src/pulse_detect.c:325-334).  While
         // |am - low| < 1024 it is low += (am > low) ? +1 : -1; with q = low + j that is
         // q += 2 * (am_j + j > q): two dependent instructions per sample.
@@ -503,19 +619,29 @@ __global__ void __launch_bounds__(kDetectWarps * 32, kDetectCtasPerSm) k_detect(
             int a = (int)(int16_t)(wv & 0xffff);
             int f = (int)(int16_t)(wv >> 16);
             int aq = a / 64, fq = f / 64;
-            int h = d.high, g = d.ook_f1;
-            int myh = h, myg = g;
-#pragma unroll 8
-            for (int j = 0; j < cnt; ++j) {
-                if (lane == j) {
-                    myh = h;
-                    myg = g;
+            int h = d.high, g = d.ook_f1; // h >= min_high >= 0 here, so h / 64 == h >> 6
+            int myh = h;
+            int const minh = p.lv.min_high;
+            if (cnt == 32) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    myh = lane == j ? h : myh;
+                    int aj = __shfl_sync(0xffffffffu, aq, j);
+                    int fj = __shfl_sync(0xffffffffu, fq, j);
+                    h += aj - (int)((unsigned)h >> 6);
+                    h = h < minh ? minh : h;
+                    g += fj - g / 64;
                 }
-                int aj = __shfl_sync(0xffffffffu, aq, j);
-                int fj = __shfl_sync(0xffffffffu, fq, j);
-                h += aj - h / 64;
-                if (h < p.lv.min_high) h = p.lv.min_high;
-                g += fj - g / 64;
+            } else {
+#pragma unroll 4
+                for (int j = 0; j < cnt; ++j) {
+                    myh = lane == j ? h : myh;
+                    int aj = __shfl_sync(0xffffffffu, aq, j);
+                    int fj = __shfl_sync(0xffffffffu, fq, j);
+                    h += aj - (int)((unsigned)h >> 6);
+                    h = h < minh ? minh : h;
+                    g += fj - g / 64;
+                }
             }
             Thresholds th = det_thresholds(d.low, myh, p.lv);
             unsigned m = __ballot_sync(0xffffffffu, lane < cnt && a < th.down);
@@ -527,15 +653,21 @@ __global__ void __launch_bounds__(kDetectWarps * 32, kDetectCtasPerSm) k_detect(
             }
             int jb = __ffs(m) - 1;
             d.high = __shfl_sync(0xffffffffu, myh, jb);
-            d.ook_f1 = __shfl_sync(0xffffffffu, myg, jb);
+            // the carrier estimate in front of sample jb: redo its (cheap) recurrence up to there
+            g = d.ook_f1;
+#pragma unroll 4
+            for (int j = 0; j < jb; ++j) g += __shfl_sync(0xffffffffu, fq, j) - g / 64;
+            d.ook_f1 = g;
             d.run += jb;
             return jb; // sample jb ends the pulse: det_step() takes it
         };
 
         for (int n = 0; n < nv_tile;) {
             int adv = 0;
-            if (d.st == kIdle)
-                adv = idle_fast(n);
+            if (d.st == kIdle) {
+                adv = idle_tile(n);
+                if (!adv) adv = idle_fast(n);
+            }
             else if (d.st == kGap)
                 adv = gap_fast(n);
             else if (d.st == kPulse)
