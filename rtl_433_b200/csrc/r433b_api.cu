@@ -343,6 +343,13 @@ int r433b_process(r433b_ctx *ctx, r433b_batch const *b)
     auto by_mod = [&](unsigned a, unsigned c) {
         // lanes of a warp should walk the same code: same slicer, then similar event cadence
         r433b_device const &x = ctx->devs[a], &y = ctx->devs[c];
+        static int const mode = getenv("R433B_SORT") ? atoi(getenv("R433B_SORT")) : 0; // tuning experiments only
+        if (mode == 1) { // event cadence first, slicer second
+            if (x.reset_limit != y.reset_limit) return x.reset_limit < y.reset_limit;
+            if (x.modulation != y.modulation) return x.modulation < y.modulation;
+            return a < c;
+        }
+        if (mode == 2) return a < c; // registration order
         if (x.modulation != y.modulation) return x.modulation < y.modulation;
         if (x.reset_limit != y.reset_limit) return x.reset_limit < y.reset_limit;
         if (x.short_width != y.short_width) return x.short_width < y.short_width;

@@ -26,6 +26,21 @@
 #include "r433b_core.cuh"
 #include "r433b_slice.cuh"
 
+#ifndef R4_UNROLL_IIR
+#define R4_UNROLL_IIR 2
+#endif
+#ifndef R4_UNROLL_TILE
+#define R4_UNROLL_TILE 2
+#endif
+#ifndef R4_UNROLL_IDLE
+#define R4_UNROLL_IDLE 4
+#endif
+#ifndef R4_UNROLL_PULSE
+#define R4_UNROLL_PULSE 2
+#endif
+#define R4_PRAGMA(x) _Pragma(#x)
+#define R4_UNROLL(n) R4_PRAGMA(unroll n)
+
 namespace r433b {
 
 constexpr int kTrainInts = 4 * kMaxPulses; // per-stream scratch: ook pulse/gap, fsk pulse/gap
@@ -301,7 +316,7 @@ __global__ void __launch_bounds__(kDetectWarps * 32, kDetectCtasPerSm) k_detect(
         // both ends of both brackets advance together: four independent dependency chains
         auto run_chunk2 = [&](int &ya0, int &ya1, int &yf0, int &yf1) {
             int xp = xl, fp = fl;
-#pragma unroll 4
+R4_UNROLL(R4_UNROLL_IIR)
             for (int k = 0; k < nv; ++k) {
                 uint32_t w0 = mine[k * W];
                 int x = (int)(w0 & 0xffff);
@@ -362,7 +377,7 @@ __global__ void __launch_bounds__(kDetectWarps * 32, kDetectCtasPerSm) k_detect(
             int ya = lo_a, yf = lo_f;
             int xp = xl, fp = fl;
             unsigned long long const gbase = sample0 + t0 + (unsigned long long)lane * C;
-#pragma unroll 4
+R4_UNROLL(R4_UNROLL_IIR)
             for (int k = 0; k < nv; ++k) {
                 uint32_t w0 = mine[k * W];
                 int x = (int)(w0 & 0xffff);
@@ -431,7 +446,7 @@ __global__ void __launch_bounds__(kDetectWarps * 32, kDetectCtasPerSm) k_detect(
             uint32_t const *chunk = tile + lane * (W * C + 1);
             int cmin = 32767, cmax = -32768;
             if (in_region) {
-#pragma unroll 4
+R4_UNROLL(R4_UNROLL_TILE)
                 for (int k = k0; k < k1; ++k) {
                     int a = (int)(int16_t)(chunk[k * W] & 0xffff);
                     cmin = a < cmin ? a : cmin;
@@ -494,7 +509,7 @@ __global__ void __launch_bounds__(kDetectWarps * 32, kDetectCtasPerSm) k_detect(
             for (int round = 0; round < 8; ++round) {
                 int elo = lo, ehi = hi;
                 if (act) {
-#pragma unroll 4
+R4_UNROLL(R4_UNROLL_TILE)
                     for (int k = k0; k < k1; ++k) {
                         int a = (int)(int16_t)(chunk[k * W] & 0xffff);
                         elo += a > elo ? 1 : -1;
@@ -546,18 +561,10 @@ __global__ void __launch_bounds__(kDetectWarps * 32, kDetectCtasPerSm) k_detect(
             if (cnt == 0) return 0;
             int q = d.low;
             int b = a + lane;
-            if (cnt == 32) {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    int bj = __shfl_sync(0xffffffffu, b, j);
-                    if (bj > q) q += 2;
-                }
-            } else {
-#pragma unroll 4
-                for (int j = 0; j < cnt; ++j) {
-                    int bj = __shfl_sync(0xffffffffu, b, j);
-                    if (bj > q) q += 2;
-                }
+R4_UNROLL(R4_UNROLL_IDLE)
+            for (int j = 0; j < cnt; ++j) {
+                int bj = __shfl_sync(0xffffffffu, b, j);
+                if (bj > q) q += 2;
             }
             d.low = q - cnt;
             int hh = p.lv.ratio * d.low;
@@ -622,26 +629,14 @@ __global__ void __launch_bounds__(kDetectWarps * 32, kDetectCtasPerSm) k_detect(
             int h = d.high, g = d.ook_f1; // h >= min_high >= 0 here, so h / 64 == h >> 6
             int myh = h;
             int const minh = p.lv.min_high;
-            if (cnt == 32) {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    myh = lane == j ? h : myh;
-                    int aj = __shfl_sync(0xffffffffu, aq, j);
-                    int fj = __shfl_sync(0xffffffffu, fq, j);
-                    h += aj - (int)((unsigned)h >> 6);
-                    h = h < minh ? minh : h;
-                    g += fj - g / 64;
-                }
-            } else {
-#pragma unroll 4
-                for (int j = 0; j < cnt; ++j) {
-                    myh = lane == j ? h : myh;
-                    int aj = __shfl_sync(0xffffffffu, aq, j);
-                    int fj = __shfl_sync(0xffffffffu, fq, j);
-                    h += aj - (int)((unsigned)h >> 6);
-                    h = h < minh ? minh : h;
-                    g += fj - g / 64;
-                }
+R4_UNROLL(R4_UNROLL_PULSE)
+            for (int j = 0; j < cnt; ++j) {
+                myh = lane == j ? h : myh;
+                int aj = __shfl_sync(0xffffffffu, aq, j);
+                int fj = __shfl_sync(0xffffffffu, fq, j);
+                h += aj - (int)((unsigned)h >> 6);
+                h = h < minh ? minh : h;
+                g += fj - g / 64;
             }
             Thresholds th = det_thresholds(d.low, myh, p.lv);
             unsigned m = __ballot_sync(0xffffffffu, lane < cnt && a < th.down);
@@ -662,6 +657,25 @@ __global__ void __launch_bounds__(kDetectWarps * 32, kDetectCtasPerSm) k_detect(
             return jb; // sample jb ends the pulse: det_step() takes it
         };
 
+        // GAP_START after the first pulse (no FSK feed): thresholds are frozen and nothing happens
+        // until either a sample rises above `up` (spurious gap) or the run reaches 10 samples.
+        // Skip the uneventful samples in front of that transition; det_step() takes the transition.
+        auto gapstart_fast = [&](int n) -> int {
+            if (d.ook_n == 0) return 0;
+            int quiet = kMinPulseSamples - 1 - d.run; // samples that can pass without reaching 10
+            if (quiet <= 0) return 0;
+            int cnt = nv_tile - n < quiet ? nv_tile - n : quiet;
+            Thresholds th = det_thresholds(d.low, d.high, p.lv);
+            int a = lane < cnt ? (int)(int16_t)(tile[word_index<C, W>(n + lane)] & 0xffff) : -32768;
+            unsigned m = __ballot_sync(0xffffffffu, lane < cnt && a > th.up);
+            if (m) {
+                int ja = __ffs(m) - 1;
+                cnt = ja < cnt ? ja : cnt;
+            }
+            d.run += cnt;
+            return cnt;
+        };
+
         for (int n = 0; n < nv_tile;) {
             int adv = 0;
             if (d.st == kIdle) {
@@ -672,6 +686,8 @@ __global__ void __launch_bounds__(kDetectWarps * 32, kDetectCtasPerSm) k_detect(
                 adv = gap_fast(n);
             else if (d.st == kPulse)
                 adv = pulse_fast(n);
+            else
+                adv = gapstart_fast(n);
             if (adv) {
                 n += adv;
                 continue;

@@ -75,6 +75,7 @@ struct EventWriter {
     uint32_t *out;      // pair region, or nullptr while counting
     unsigned limit;     // words the counting pass committed: rows of a trailing, never-emitted
                         // event lie beyond it and must not be written
+
     unsigned pos;       // words used by finished events + the current event so far
     unsigned committed; // words up to the end of the last emitted event
     unsigned events;
@@ -162,6 +163,17 @@ struct EventWriter {
     R4_HD void add_bits(int value, int count)
     {
         first_row();
+        {
+            // common case: the run ends inside the current word and the row neither starts on nor
+            // crosses a 1024-bit spill boundary, nor comes near the 65535-bit limit
+            unsigned const p = bits & 31, in_row = bits & (kBbCols * 8 - 1);
+            if ((unsigned)count <= 32 - p && (in_row != 0 || bits == 0) && bits < 60000u) {
+                if (value) acc |= (0xffffffffu >> (32 - count)) << (32 - p - count);
+                bits += (unsigned)count;
+                if ((bits & 31) == 0) flush_word();
+                return;
+            }
+        }
         while (count > 0) {
             if (bits == 65535u) return; // row length limit: further bits are dropped
             if (bits > 0 && (bits & (kBbCols * 8 - 1)) == 0) { // spill into the next physical row

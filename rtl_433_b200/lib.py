@@ -13,7 +13,7 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-LIB_PATH = os.path.join(CSRC, "libr433b.so")
+LIB_PATH = os.environ.get("R433B_LIB") or os.path.join(CSRC, "libr433b.so")  # override: tuning experiments only
 
 FMT_CU8, FMT_CS16 = 2, 4
 FPDM_CLASSIC, FPDM_MINMAX, FPDM_AUTO = 0, 1, 2
