@@ -235,10 +235,10 @@ int r433b_set_r_devices(r433b_ctx *ctx, struct r_device *const *devs, uint32_t n
 int r433b_process(r433b_ctx *ctx, r433b_batch const *b)
 {
     if (!ctx || !b || !b->offsets || (b->n_streams && !b->data)) return fail(ctx, R433B_EINVAL, "null argument");
-    if (b->sample_format != R433B_FMT_CU8 && b->sample_format != R433B_FMT_CS16)
-        return fail(ctx, R433B_EINVAL, "sample_format must be 2 (cu8) or 4 (cs16)");
+    if (b->sample_format != R433B_FMT_CU8 && b->sample_format != R433B_FMT_CS16 && b->sample_format != R433B_FMT_CS8)
+        return fail(ctx, R433B_EINVAL, "sample_format must be R433B_FMT_CU8, _CS8 or _CS16");
     if (b->samp_rate == 0) return fail(ctx, R433B_EINVAL, "samp_rate is 0");
-    int const SS = (int)b->sample_format;
+    int const SS = (int)(b->sample_format & 0xff); // bytes per IQ sample; cs8 is cu8 after the load-time +128
     uint32_t block_bytes = b->block_bytes ? b->block_bytes : 262144u;
     int const T = SS == 2 ? TileCfg<2>::T : TileCfg<4>::T;
     if (block_bytes % (uint32_t)(T * SS) != 0) return fail(ctx, R433B_EINVAL, "block_bytes must be a multiple of 2048");
@@ -249,6 +249,7 @@ int r433b_process(r433b_ctx *ctx, r433b_batch const *b)
     CU(cudaSetDevice(ctx->device));
     ctx->processed = ctx->fetched = false;
     ctx->batch = *b;
+    ctx->batch.sample_format = (uint32_t)SS; // the host replay only needs the sample size (dm_state.sample_size)
     ctx->batch.block_bytes = block_bytes;
     ctx->offsets.assign(b->offsets, b->offsets + b->n_streams + 1);
     ctx->batch.offsets = ctx->offsets.data();
@@ -293,6 +294,7 @@ int r433b_process(r433b_ctx *ctx, r433b_batch const *b)
     dp.first_chunk = 1;
     dp.state = nullptr;
     dp.use_mag = ctx->use_mag;
+    dp.flip = b->sample_format == R433B_FMT_CS8 ? 0x80808080u : 0u;
     dp.enable_fm = ctx->enable_fm;
     dp.fpdm = (int)ctx->fpdm;
     dp.rate = b->samp_rate;

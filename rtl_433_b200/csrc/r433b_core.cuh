@@ -90,6 +90,25 @@ R4_HD int atan16(int y, int x)
     return (int)(int16_t)(y < 0 ? -ang : ang);
 }
 
+// t / den with C semantics for |t| < 2^62, 1 <= den < 2^33 and |t / den| < 2^30.  On the
+// device: double-precision reciprocal estimate (quotient error < 2^-20) plus one exact 64-bit
+// correction step, instead of the ~100-instruction generic 64-bit division.
+R4_HD long long div_trunc_big(long long t, long long den)
+{
+#ifdef __CUDA_ARCH__
+    unsigned long long u = (unsigned long long)(t < 0 ? -t : t);
+    long long q = (long long)__dmul_rn((double)u, __drcp_rn((double)den));
+    long long r = (long long)u - q * den;
+    if (r < 0)
+        q -= 1;
+    else if (r >= den)
+        q += 1;
+    return t < 0 ? -q : q;
+#else
+    return t / den;
+#endif
+}
+
 // src/baseband.c:281-300: pi == INT32_MAX, no (0,0) case, arguments already narrowed to int32
 R4_HD int atan32(int y, int x)
 {
@@ -99,11 +118,11 @@ R4_HD int atan32(int y, int x)
     if (x >= 0) {
         long long d = ay + x;
         if (d == 0) d = 1;
-        ang = q - q * (x - ay) / d;
+        ang = q - div_trunc_big(q * (x - ay), d);
     } else {
         long long d = ay - x;
         if (d == 0) d = 1;
-        ang = q3 - q * (x + ay) / d;
+        ang = q3 - div_trunc_big(q * (x + ay), d);
     }
     return (int)(y < 0 ? -ang : ang);
 }

@@ -65,6 +65,7 @@ struct DetectParams {
     int first_chunk;              // start from reset_sdr_flow() state instead of the saved one
     struct StreamState *state;    // per-stream carried state between launches of one batch
     int use_mag, enable_fm, fpdm;
+    unsigned flip; // XOR mask applied to every loaded word: 0x80808080 turns cs8 into cu8
     unsigned rate, block_samples;
     Levels lv;
     int lpf_a1, lpf_b0, fm_a1, fm_b0;
@@ -232,13 +233,13 @@ __global__ void __launch_bounds__(kDetectWarps * 32, kDetectCtasPerSm) k_detect(
             uint8_t const *g = src + (t0 + (unsigned long long)n0) * SS;
             if (n0 + SPL <= nv_tile) {
                 uint4 v = __ldg(reinterpret_cast<uint4 const *>(g));
-                rw[0] = v.x;
-                rw[1] = v.y;
-                rw[2] = v.z;
-                rw[3] = v.w;
+                rw[0] = v.x ^ p.flip;
+                rw[1] = v.y ^ p.flip;
+                rw[2] = v.z ^ p.flip;
+                rw[3] = v.w ^ p.flip;
             } else if (n0 < nv_tile) { // ragged end of the stream
                 int nb = (nv_tile - n0) * SS;
-                for (int bidx = 0; bidx < nb; ++bidx) rw[bidx >> 2] |= (uint32_t)g[bidx] << (8 * (bidx & 3));
+                for (int bidx = 0; bidx < nb; ++bidx) rw[bidx >> 2] |= (uint32_t)(g[bidx] ^ (p.flip & 0xff)) << (8 * (bidx & 3));
             }
             int li, lq; // last sample of this lane's group, for the lane to the right
             if (SS == 2) {

@@ -167,3 +167,17 @@ def test_pipelined_time_slices_identical(ctx, devices):
                 assert not d, "\n".join(d[:20])
     finally:
         ctx.set_pipeline(0)
+
+
+def test_cs8_input_is_cu8_plus_128(ctx, devices):
+    """cs8 captures are converted to cu8 (+128, src/rtl_433.c:1830-1834) inside the load phase."""
+    streams = [synth.ook_stream(31), synth.ook_stream(32)[: 2 * 16 * 40001]]
+    o = oracle_for(devices, stages=False)
+    lens = [s.nbytes for s in streams]
+    offsets = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
+    as_cs8 = np.concatenate(streams) ^ np.uint8(0x80)  # the int8 bytes a .cs8 file would hold
+    ctx.process(as_cs8, offsets, lib.FMT_CS8, 250000, 433920000)
+    ctx.fetch()
+    for i, s in enumerate(streams):
+        d = helpers.compare_results(o.run(s, 2), helpers.gpu_stream_results(ctx, i), f"cs8 {i}", stages=False)
+        assert not d, "\n".join(d[:20])
