@@ -285,7 +285,8 @@ def run_gpu(a, w):
         pkg_bytes = counts["packages"] * 72 + 8 * (counts["packages"] * 140)  # headers + ~pulse/gap widths
         alg_bytes = samples_step * fmt + pkg_bytes
         achieved = alg_bytes / (det * 1e-3) / 1e9
-        traffic = recorded_traffic()
+        # the recorded ncu capture is of the default OOK workload only
+        traffic = recorded_traffic() if (a.workload == "ook_cu8_250k" and streams == w["streams"]) else None
         line = {
             "metric": "IQ MS/s end-to-end demod+slice", "value": round(value, 1), "unit": "MS/s", "n_gpus": world,
             "steps": a.steps, "warmup": a.warmup, "ms_per_step": round(dev_ms_max / a.steps, 3), "higher_is_better": True,
