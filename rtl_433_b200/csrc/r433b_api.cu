@@ -389,9 +389,10 @@ int r433b_process(r433b_ctx *ctx, r433b_batch const *b)
         q.cursor = (unsigned long long *)ctx->d_cursor.p;
     };
 
-    // ---- pipelined path: host input cut into G TIME SLICES of every stream; copy-in of slice
-    //      k+1, detect of slice k, slicing of the packages slice k-1 completed and copy-out overlap
-    //      on four streams.  (Cutting by streams instead does not help: a warp needs the same
+    // ---- pipelined path: host input cut into G TIME SLICES of every stream; the copy-in of slice
+    //      k+1 and the copy-out of finished ranges overlap the kernels of slice k (three streams).
+    //      detect(k) and slice(k) stay on ONE stream: both are issue-bound, running them
+    //      concurrently only makes each slower (measured).  (Cutting by streams instead does not help: a warp needs the same
     //      wall time for its stream however few other warps run.)  Detector / filter state is
     //      carried between launches in `StreamState`; results are identical to one launch. ----
     int G = ctx->pipeline_groups;
@@ -401,7 +402,8 @@ int r433b_process(r433b_ctx *ctx, r433b_batch const *b)
         if (ctx->offsets[i + 1] - ctx->offsets[i] != stride) uniform = false;
     if (G == 0) // measured on B200: 8 slices of >= 256 KiB per stream beat fewer, larger ones
         G = (total_bytes >= (256ull << 20) && stride >= (1u << 20)) ? (int)std::min<uint64_t>(8, stride / (256u << 10)) : 1;
-    if (b->data_on_device || b->want_stages || !n_devs || !uniform) G = 1;
+    if (b->data_on_device && ctx->pipeline_groups == 0) G = 1; // device input: slices only when asked for
+    if (b->want_stages || !n_devs || !uniform) G = 1;
     uint64_t slice_samples = 0;
     if (G > 1) {
         uint64_t n_samp = stride / SS;
@@ -441,13 +443,13 @@ int r433b_process(r433b_ctx *ctx, r433b_batch const *b)
         CU(cudaMemsetAsync(ctx->d_cursor.p, 0, 64, ctx->s_det));
         CU(cudaMemsetAsync(ctx->d_pairs.p, 0, pair_cap_bytes, ctx->s_det));
         CU(cudaEventRecord(ctx->ev_init, ctx->s_det));
-        CU(cudaStreamWaitEvent(ctx->s_slc, ctx->ev_init, 0));
         for (int g = 0; g < G; ++g) {
             uint64_t c0 = (uint64_t)g * slice_samples * SS, c1 = std::min<uint64_t>(stride, c0 + slice_samples * SS);
             // one strided copy: the same byte range of every stream
-            CU(cudaMemcpy2DAsync((uint8_t *)ctx->d_data.p + ctx->offsets[0] + c0, stride,
-                    (uint8_t const *)b->data + ctx->offsets[0] + c0, stride, c1 - c0, b->n_streams,
-                    cudaMemcpyHostToDevice, ctx->s_in));
+            if (!b->data_on_device)
+                CU(cudaMemcpy2DAsync((uint8_t *)ctx->d_data.p + ctx->offsets[0] + c0, stride,
+                        (uint8_t const *)b->data + ctx->offsets[0] + c0, stride, c1 - c0, b->n_streams,
+                        cudaMemcpyHostToDevice, ctx->s_in));
             CU(cudaEventRecord(ctx->ev_in[g], ctx->s_in));
             CU(cudaStreamWaitEvent(ctx->s_det, ctx->ev_in[g], 0));
             k_mark<<<1, 1, 0, ctx->s_det>>>(d_rg + g, 0, d_cnt, d_cur);
@@ -460,21 +462,20 @@ int r433b_process(r433b_ctx *ctx, r433b_batch const *b)
             CU(cudaEventRecord(ctx->ev_t[4 * g + 1], ctx->s_det));
             k_mark<<<1, 1, 0, ctx->s_det>>>(d_rg + g, 1, d_cnt, d_cur);
             CU(cudaEventRecord(ctx->ev_det[g], ctx->s_det));
-            CU(cudaStreamWaitEvent(ctx->s_slc, ctx->ev_det[g], 0));
-            k_mark<<<1, 1, 0, ctx->s_slc>>>(d_rg + g, 2, d_cnt, d_cur);
-            CU(cudaEventRecord(ctx->ev_t[4 * g + 2], ctx->s_slc));
+            k_mark<<<1, 1, 0, ctx->s_det>>>(d_rg + g, 2, d_cnt, d_cur);
+            CU(cudaEventRecord(ctx->ev_t[4 * g + 2], ctx->s_det));
             SliceParams qg = q;
             qg.range = d_rg + g;
-            k_slice<<<148 * 8, kSliceThreads, 0, ctx->s_slc>>>(qg);
-            CU(cudaEventRecord(ctx->ev_t[4 * g + 3], ctx->s_slc));
-            k_mark<<<1, 1, 0, ctx->s_slc>>>(d_rg + g, 3, d_cnt, d_cur);
-            CU(cudaMemcpyAsync(h_rg + g, d_rg + g, sizeof(GroupRange), cudaMemcpyDeviceToHost, ctx->s_slc));
-            CU(cudaEventRecord(ctx->ev_slc[g], ctx->s_slc));
+            k_slice<<<148 * 8, kSliceThreads, 0, ctx->s_det>>>(qg);
+            CU(cudaEventRecord(ctx->ev_t[4 * g + 3], ctx->s_det));
+            k_mark<<<1, 1, 0, ctx->s_det>>>(d_rg + g, 3, d_cnt, d_cur);
+            CU(cudaMemcpyAsync(h_rg + g, d_rg + g, sizeof(GroupRange), cudaMemcpyDeviceToHost, ctx->s_det));
+            CU(cudaEventRecord(ctx->ev_slc[g], ctx->s_det));
         }
         CU(cudaGetLastError());
         // copy-out of finished groups while later ones compute; only into host buffers that are
         // already large enough (they are after the first batch of a given shape)
-        bool overflow = false, d2h_ok = true;
+        bool overflow = false, d2h_ok = !b->data_on_device; // device input: results stay put until r433b_fetch()
         for (int g = 0; g < G; ++g) {
             CU(cudaEventSynchronize(ctx->ev_slc[g]));
             GroupRange const r = h_rg[g];

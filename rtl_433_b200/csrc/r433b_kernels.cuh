@@ -739,7 +739,8 @@ struct GroupRange {
     unsigned pool_begin, pool_end;
     unsigned long long arena_begin, arena_end;
     unsigned long long events_end;
-    unsigned overflow, pad;
+    unsigned overflow;
+    unsigned next; // k_slice work counter: next package of this range to hand to a CTA
 };
 
 __global__ void k_mark(GroupRange *r, int which, unsigned const *counters, unsigned long long const *cursor)
@@ -751,6 +752,7 @@ __global__ void k_mark(GroupRange *r, int which, unsigned const *counters, unsig
         r->pkg_end = counters[0];
         r->pool_end = counters[1];
         r->overflow = counters[2];
+        r->next = r->pkg_begin;
     } else if (which == 2) {
         r->arena_begin = cursor[0];
     } else {
@@ -763,7 +765,7 @@ __global__ void k_mark(GroupRange *r, int which, unsigned const *counters, unsig
 struct SliceParams {
     r433b_package *pkgs;
     unsigned n_pkgs;
-    GroupRange const *range; // if set: packages [pkg_begin, min(pkg_end, n_pkgs)) instead of [0, n_pkgs)
+    GroupRange *range; // if set: packages [pkg_begin, min(pkg_end, n_pkgs)) instead of [0, n_pkgs)
     int const *pulse_pool, *gap_pool;
     SlicerParams const *dev;  // per device, already scaled to the batch sample rate
     unsigned n_devs;
@@ -779,12 +781,22 @@ constexpr int kSliceThreads = 128;
 
 __global__ void __launch_bounds__(kSliceThreads) k_slice(SliceParams p)
 {
-    unsigned pk_begin = 0, pk_end = p.n_pkgs;
+    // Without a range: one CTA per package (the grid is the package count).  With a range (pipelined
+    // path, package count unknown to the host): a fixed grid whose CTAs fetch packages one at a time.
+    __shared__ unsigned s_pk;
+    unsigned pk_end = p.n_pkgs;
+    if (p.range) pk_end = p.range->pkg_end < p.n_pkgs ? p.range->pkg_end : p.n_pkgs;
+    for (;;) {
+    unsigned pk;
     if (p.range) {
-        pk_begin = p.range->pkg_begin;
-        pk_end = p.range->pkg_end < p.n_pkgs ? p.range->pkg_end : p.n_pkgs;
+        __syncthreads();
+        if (threadIdx.x == 0) s_pk = atomicAdd(&p.range->next, 1u);
+        __syncthreads();
+        pk = s_pk;
+    } else {
+        pk = blockIdx.x;
     }
-    for (unsigned pk = pk_begin + blockIdx.x; pk < pk_end; pk += gridDim.x) {
+    if (pk >= pk_end) break;
     r433b_package const k = p.pkgs[pk];
     unsigned const n_list = k.type == 1 ? p.n_ook : p.n_fsk;
     unsigned const *list = k.type == 1 ? p.ook_list : p.fsk_list;
@@ -848,7 +860,8 @@ __global__ void __launch_bounds__(kSliceThreads) k_slice(SliceParams p)
             p.pairs[(size_t)pk * p.n_devs + dev] = pr;
         }
     }
-    } // packages of this block
+    if (!p.range) break;
+    } // packages of this CTA
 }
 
 } // namespace r433b

@@ -20,6 +20,7 @@ ap.add_argument("--log2n", type=int, default=20)
 ap.add_argument("--fsk", action="store_true")
 ap.add_argument("--devices", default="all")
 ap.add_argument("--iters", type=int, default=3)
+ap.add_argument("--pipeline", type=int, default=0)
 a = ap.parse_args()
 
 n = 1 << a.log2n
@@ -42,13 +43,17 @@ if a.devices != "all":
     devs = devs[: int(a.devices)]
 ctx = lib.Context(0)
 ctx.set_devices(devs)
+ctx.set_pipeline(a.pipeline)
+import time as _t
 torch.cuda.synchronize()
 for it in range(a.iters):
+    torch.cuda.synchronize(); _t0 = _t.perf_counter()
     ctx.process(dev.data_ptr(), offsets, fmt, rate, freq, data_on_device=True)
+    torch.cuda.synchronize(); _wall = (_t.perf_counter() - _t0) * 1e3
     tm = ctx.timing()
     c = ctx.counts()
     ms = tm["detect_ms"] + tm["slice_ms"]
-    print(f"iter {it}: detect {tm['detect_ms']:.2f} ms  slice {tm['slice_ms']:.2f} ms  launches {tm['detect_launches']}+{tm['slice_launches']}  "
+    print(f"iter {it}: wall {_wall:.2f} ms ({c['samples'] / _wall / 1e3:.0f} MS/s) detect {tm['detect_ms']:.2f} ms  slice {tm['slice_ms']:.2f} ms  launches {tm['detect_launches']}+{tm['slice_launches']}  "
           f"packages {c['packages']} events {c['events']} event_bytes {c['event_bytes']}  "
           f"-> {c['samples'] / ms / 1e3:.1f} MS/s  detect-only {c['samples'] / tm['detect_ms'] / 1e3:.1f} MS/s "
           f"({c['samples'] * fmt / tm['detect_ms'] / 1e6:.1f} GB/s)")
