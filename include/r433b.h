@@ -67,6 +67,9 @@ typedef struct r433b_batch {
     uint32_t block_bytes;    /* 0 = 262144, the reference's DEFAULT_BUF_LENGTH */
     int32_t data_on_device;
     int32_t want_stages;     /* keep the AM/FM stage arrays on the device for r433b_copy_stage() */
+    uint64_t const *lengths; /* optional, n_streams entries: bytes of stream i actually used (<= the gap to
+                                the next offset); NULL = every stream fills its gap.  Lets files of any
+                                length sit at 16-byte aligned starts. */
 } r433b_batch;
 
 /* A detected package = the integer part of pulse_data_t (include/pulse_data.h:30-50) plus

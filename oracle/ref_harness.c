@@ -638,3 +638,14 @@ REFH_EXPORT void refh_reset_stats(refh_t *h)
         memset(d->decode_fails, 0, sizeof(d->decode_fails));
     }
 }
+
+/* file_info_parse_filename(), src/fileformat.c:298: out = {format, sample_rate, center_frequency} */
+REFH_EXPORT void refh_parse_filename(char const *name, uint32_t out[3])
+{
+    file_info_t info;
+    memset(&info, 0, sizeof(info));
+    file_info_parse_filename(&info, name);
+    out[0] = info.format;
+    out[1] = info.sample_rate;
+    out[2] = info.center_frequency;
+}

@@ -103,6 +103,7 @@ def lib():
         L.refh_begin_external_dispatch.argtypes = [C.c_void_p]
         L.refh_end_external_dispatch.argtypes = [C.c_void_p]
         L.refh_reset_stats.argtypes = [C.c_void_p]
+        L.refh_parse_filename.argtypes = [C.c_char_p, C.POINTER(C.c_uint32)]
         L.refh_envelope_detect.restype = C.c_float
         L.refh_envelope_detect.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
         L.refh_magnitude_est_cu8.restype = C.c_float
@@ -248,6 +249,16 @@ def _slice_all(self, fsk, sample_rate, pulse, gap):
 
 
 Ref.slice_all = _slice_all
+
+
+# compound file types of include/fileformat.h that the GPU path understands
+FILE_FORMATS = {0x210820: "cu8", 0x210821: "cs8", 0x211021: "cs16", 0x212023: "cf32"}
+
+
+def parse_filename(name):
+    out = (C.c_uint32 * 3)()
+    lib().refh_parse_filename(name.encode(), out)
+    return {"format_code": out[0], "format": FILE_FORMATS.get(out[0]), "sample_rate": out[1], "center_frequency": out[2]}
 
 
 def row_hex(bb, row):

@@ -45,7 +45,7 @@ struct r433b_ctx {
     std::vector<r433b_device> devs;
     // last batch (kept for the host replay)
     r433b_batch batch{};
-    std::vector<uint64_t> offsets;
+    std::vector<uint64_t> offsets, lengths; // lengths[i] = bytes of stream i in use
     bool processed = false, fetched = false;
     unsigned fpdm = 0;
     int enable_fm = 0;
@@ -67,7 +67,7 @@ struct r433b_ctx {
     cudaStream_t s_in = nullptr, s_det = nullptr, s_slc = nullptr, s_out = nullptr;
     static constexpr int kMaxGroups = 16;
     cudaEvent_t ev_in[kMaxGroups]{}, ev_det[kMaxGroups]{}, ev_slc[kMaxGroups]{}, ev_t[4 * kMaxGroups]{}, ev_init = nullptr;
-    DevBuf d_ranges, d_state;
+    DevBuf d_ranges, d_state, d_lengths;
     HostBuf h_ranges;
     bool d2h_done = false;
 };
@@ -161,7 +161,7 @@ void r433b_destroy(r433b_ctx *ctx)
     cudaSetDevice(ctx->device);
     for (DevBuf *b : {&ctx->d_data, &ctx->d_offsets, &ctx->d_train, &ctx->d_pkgs, &ctx->d_ppool, &ctx->d_gpool,
                  &ctx->d_counters, &ctx->d_am, &ctx->d_fm, &ctx->d_devparams, &ctx->d_lists, &ctx->d_pairs,
-                 &ctx->d_arena, &ctx->d_cursor, &ctx->d_ranges, &ctx->d_state})
+                 &ctx->d_arena, &ctx->d_cursor, &ctx->d_ranges, &ctx->d_state, &ctx->d_lengths})
         if (b->p) cudaFree(b->p);
     for (HostBuf *b : {&ctx->h_pkgs, &ctx->h_ppool, &ctx->h_gpool, &ctx->h_pairs, &ctx->h_events, &ctx->h_small,
                  &ctx->h_ranges})
@@ -253,7 +253,16 @@ int r433b_process(r433b_ctx *ctx, r433b_batch const *b)
     ctx->batch.block_bytes = block_bytes;
     ctx->offsets.assign(b->offsets, b->offsets + b->n_streams + 1);
     ctx->batch.offsets = ctx->offsets.data();
+    ctx->lengths.resize(b->n_streams);
+    for (uint32_t i = 0; i < b->n_streams; ++i) {
+        uint64_t gap = b->offsets[i + 1] - b->offsets[i];
+        ctx->lengths[i] = b->lengths ? b->lengths[i] : gap;
+        if (ctx->lengths[i] > gap) return fail(ctx, R433B_EINVAL, "lengths[i] exceeds the gap to the next offset");
+    }
+    ctx->batch.lengths = ctx->lengths.data();
     uint64_t const total_bytes = b->n_streams ? b->offsets[b->n_streams] : 0;
+    uint64_t used_bytes = 0;
+    for (uint64_t v : ctx->lengths) used_bytes += v;
     uint32_t const n_devs = (uint32_t)ctx->devs.size();
 
     // src/rtl_433.c:1094-1102 and :1515-1522
@@ -275,6 +284,8 @@ int r433b_process(r433b_ctx *ctx, r433b_batch const *b)
     }
     if (int r = dev_reserve(ctx, ctx->d_offsets, (b->n_streams + 1) * sizeof(uint64_t))) return r;
     CU(cudaMemcpy(ctx->d_offsets.p, ctx->offsets.data(), (b->n_streams + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice));
+    if (int r = dev_reserve(ctx, ctx->d_lengths, std::max<size_t>(1, b->n_streams) * sizeof(uint64_t))) return r;
+    if (b->n_streams) CU(cudaMemcpy(ctx->d_lengths.p, ctx->lengths.data(), b->n_streams * sizeof(uint64_t), cudaMemcpyHostToDevice));
     if (int r = dev_reserve(ctx, ctx->d_train, (size_t)std::max(1u, b->n_streams) * kTrainInts * sizeof(int))) return r;
     if (int r = dev_reserve(ctx, ctx->d_counters, 64)) return r;
     if (int r = dev_reserve(ctx, ctx->d_cursor, 64)) return r;
@@ -286,6 +297,7 @@ int r433b_process(r433b_ctx *ctx, r433b_batch const *b)
     DetectParams dp{};
     dp.data = d_in;
     dp.offsets = (unsigned long long const *)ctx->d_offsets.p;
+    dp.lengths = (unsigned long long const *)ctx->d_lengths.p;
     dp.n_streams = b->n_streams;
     dp.stream0 = 0;
     dp.stream_end = b->n_streams;
@@ -399,15 +411,15 @@ int r433b_process(r433b_ctx *ctx, r433b_batch const *b)
     uint64_t stride = b->n_streams ? ctx->offsets[1] - ctx->offsets[0] : 0;
     bool uniform = b->n_streams > 0 && stride > 0;
     for (uint32_t i = 0; uniform && i < b->n_streams; ++i)
-        if (ctx->offsets[i + 1] - ctx->offsets[i] != stride) uniform = false;
-    if (G == 0) // measured on B200: 8 slices of >= 256 KiB per stream beat fewer, larger ones
-        G = (total_bytes >= (256ull << 20) && stride >= (1u << 20)) ? (int)std::min<uint64_t>(8, stride / (256u << 10)) : 1;
+        if (ctx->offsets[i + 1] - ctx->offsets[i] != stride || ctx->lengths[i] != stride) uniform = false;
+    if (G == 0) // measured on B200 (tools/e2e_sweep.py): many slices of >= 128 KiB per stream beat fewer, larger ones
+        G = (total_bytes >= (256ull << 20) && stride >= (1u << 20)) ? (int)std::min<uint64_t>(r433b_ctx::kMaxGroups, stride / (128u << 10)) : 1;
     if (b->data_on_device && ctx->pipeline_groups == 0) G = 1; // device input: slices only when asked for
     if (b->want_stages || !n_devs || !uniform) G = 1;
     uint64_t slice_samples = 0;
     if (G > 1) {
         uint64_t n_samp = stride / SS;
-        uint64_t unit = std::max<uint64_t>((uint64_t)T, dp.block_samples); // keep slices block aligned
+        uint64_t unit = (uint64_t)T; // slices only have to be tile aligned: block effects use absolute positions
         slice_samples = (n_samp / G + unit - 1) / unit * unit;
         if (slice_samples == 0 || slice_samples >= n_samp) G = 1;
         else G = (int)((n_samp + slice_samples - 1) / slice_samples);
@@ -506,7 +518,7 @@ int r433b_process(r433b_ctx *ctx, r433b_batch const *b)
             ctx->pool_used = last.pool_end;
             ctx->event_bytes = last.arena_end;
             ctx->n_events = last.events_end;
-            ctx->n_samples = total_bytes / SS;
+            ctx->n_samples = used_bytes / SS;
             ctx->d2h_done = d2h_ok;
             float det = 0, slc = 0;
             for (int g = 0; g < G; ++g) {
@@ -595,7 +607,7 @@ int r433b_process(r433b_ctx *ctx, r433b_batch const *b)
     }
     ctx->event_bytes = cursor[0];
     ctx->n_events = cursor[1];
-    ctx->n_samples = total_bytes / SS;
+    ctx->n_samples = used_bytes / SS;
     CU(cudaEventRecord(ctx->ev[3], st));
     CU(cudaEventSynchronize(ctx->ev[3]));
     cudaEventElapsedTime(&ctx->timing.h2d_ms, ctx->ev[0], ctx->ev[1]);
@@ -684,7 +696,7 @@ int r433b_copy_stage(r433b_ctx *ctx, uint32_t stream, int16_t *am, int16_t *fm, 
     CU(cudaSetDevice(ctx->device));
     uint64_t SS = ctx->batch.sample_format;
     uint64_t first = ctx->offsets[stream] / SS;
-    uint64_t n = (ctx->offsets[stream + 1] - ctx->offsets[stream]) / SS;
+    uint64_t n = ctx->lengths[stream] / SS;
     if (n > max_samples) n = max_samples;
     if (n) {
         CU(cudaMemcpy(am, (int16_t const *)ctx->d_am.p + first, n * sizeof(int16_t), cudaMemcpyDeviceToHost));
@@ -706,7 +718,7 @@ float r433b_package_file_pos(r433b_ctx const *ctx, r433b_results const *res, uin
     if (!ctx || !res || package >= res->n_packages) return 0.0f;
     r433b_package const &k = res->packages[package];
     uint64_t SS = ctx->batch.sample_format;
-    uint64_t bytes = ctx->offsets[k.stream + 1] - ctx->offsets[k.stream];
+    uint64_t bytes = ctx->lengths[k.stream];
     uint32_t bb = ctx->batch.block_bytes;
     uint64_t n_blocks = (bytes + bb - 1) / bb;
     if (n_blocks == 0) return 0.0f;

@@ -59,6 +59,7 @@ struct StreamState {
 struct DetectParams {
     uint8_t const *data;
     unsigned long long const *offsets; // bytes, n_streams + 1
+    unsigned long long const *lengths; // optional: bytes of stream i actually used
     unsigned n_streams;
     unsigned stream0, stream_end; // the streams this launch covers
     unsigned long long sample_begin, sample_end; // the slice of every stream this launch covers (multiples of the tile)
@@ -124,7 +125,7 @@ __global__ void __launch_bounds__(kDetectWarps * 32, kDetectCtasPerSm) k_detect(
     bool const fm_on = p.enable_fm != 0;
 
     unsigned long long const byte0 = p.offsets[s];
-    unsigned long long const N = (p.offsets[s + 1] - byte0) / SS;
+    unsigned long long const N = (p.lengths ? p.lengths[s] : p.offsets[s + 1] - byte0) / SS;
     uint8_t const *src = p.data + byte0;
     unsigned long long const sample0 = byte0 / SS;
 

@@ -51,7 +51,7 @@ class Batch(C.Structure):
     _fields_ = [("data", C.c_void_p), ("offsets", C.POINTER(C.c_uint64)), ("n_streams", C.c_uint32),
                 ("sample_format", C.c_uint32), ("samp_rate", C.c_uint32), ("center_frequency", C.c_uint32),
                 ("fpdm_mode", C.c_uint32), ("block_bytes", C.c_uint32), ("data_on_device", C.c_int32),
-                ("want_stages", C.c_int32)]
+                ("want_stages", C.c_int32), ("lengths", C.POINTER(C.c_uint64))]
 
 
 class Package(C.Structure):
@@ -187,7 +187,7 @@ class Context:
         self.n_devices = len(devs)
 
     def process(self, data, offsets, sample_format, samp_rate=250000, center_frequency=433920000, fpdm_mode=FPDM_AUTO,
-                block_bytes=0, data_on_device=False, want_stages=False):
+                block_bytes=0, data_on_device=False, want_stages=False, lengths=None):
         """`data`: host numpy array (any dtype, contiguous) or an int device pointer."""
         offs = np.ascontiguousarray(offsets, dtype=np.uint64)
         if isinstance(data, int):
@@ -195,9 +195,11 @@ class Context:
         else:
             data = np.ascontiguousarray(data)
             ptr = data.ctypes.data
+        lens = None if lengths is None else np.ascontiguousarray(lengths, dtype=np.uint64)
         b = Batch(ptr, offs.ctypes.data_as(C.POINTER(C.c_uint64)), len(offs) - 1, sample_format, samp_rate,
-                  center_frequency, fpdm_mode, block_bytes, int(data_on_device), int(want_stages))
-        self._keep = (data, offs)
+                  center_frequency, fpdm_mode, block_bytes, int(data_on_device), int(want_stages),
+                  None if lens is None else lens.ctypes.data_as(C.POINTER(C.c_uint64)))
+        self._keep = (data, offs, lens)
         self._check(self.L.r433b_process(self.h, C.byref(b)))
 
     def counts(self):

@@ -15,7 +15,7 @@ for i in range(streams):
 offsets = np.arange(streams + 1, dtype=np.uint64) * np.uint64(per)
 ctx = lib.Context(0)
 ctx.set_devices(lib.default_device_table())
-for G in [1, 2, 3, 4, 6, 8]:
+for G in [8, 12, 16]:
     ctx.set_pipeline(G)
     for it in range(3):
         torch.cuda.synchronize()
