@@ -336,7 +336,7 @@ def main():
     ap.add_argument("--streams", type=int, default=0, help="streams per GPU (default: the workload's)")
     ap.add_argument("--distinct", type=int, default=256, help="distinct seeded streams per GPU, tiled to --streams")
     ap.add_argument("--e2e-steps", type=int, default=2)
-    ap.add_argument("--ref-streams-per-core", type=int, default=192,
+    ap.add_argument("--ref-streams-per-core", type=int, default=96,
                     help="stream passes per host core in the reference/cpu_baseline leg (~22 ms each)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--pipeline", type=int, default=0, help="host-input pipeline groups (0 auto, 1 off)")

@@ -59,12 +59,12 @@ struct r433b_ctx {
     unsigned n_pkgs = 0, pool_used = 0;
     unsigned long long event_bytes = 0, n_events = 0, n_samples = 0;
     // pinned host result buffers
-    HostBuf h_pkgs, h_ppool, h_gpool, h_pairs, h_events, h_small;
+    HostBuf h_pkgs, h_ppool, h_gpool, h_pairs, h_events;
     r433b_timing timing{};
     cudaEvent_t ev[6]{};
     // pipelined path (host input): copy-in / detect / slice / copy-out streams and per-group events
     int pipeline_groups = 0; // 0 = automatic, 1 = off
-    cudaStream_t s_in = nullptr, s_det = nullptr, s_slc = nullptr, s_out = nullptr;
+    cudaStream_t s_in = nullptr, s_det = nullptr, s_out = nullptr;
     static constexpr int kMaxGroups = 16;
     cudaEvent_t ev_in[kMaxGroups]{}, ev_det[kMaxGroups]{}, ev_slc[kMaxGroups]{}, ev_t[4 * kMaxGroups]{}, ev_init = nullptr;
     DevBuf d_ranges, d_state, d_lengths;
@@ -143,7 +143,6 @@ int r433b_create(int cuda_device, r433b_ctx **out)
     for (auto &v : ctx->ev) cudaEventCreate(&v);
     cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking);
     cudaStreamCreateWithFlags(&ctx->s_det, cudaStreamNonBlocking);
-    cudaStreamCreateWithFlags(&ctx->s_slc, cudaStreamNonBlocking);
     cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking);
     for (auto &v : ctx->ev_in) cudaEventCreateWithFlags(&v, cudaEventDisableTiming);
     for (auto &v : ctx->ev_det) cudaEventCreateWithFlags(&v, cudaEventDisableTiming);
@@ -163,8 +162,7 @@ void r433b_destroy(r433b_ctx *ctx)
                  &ctx->d_counters, &ctx->d_am, &ctx->d_fm, &ctx->d_devparams, &ctx->d_lists, &ctx->d_pairs,
                  &ctx->d_arena, &ctx->d_cursor, &ctx->d_ranges, &ctx->d_state, &ctx->d_lengths})
         if (b->p) cudaFree(b->p);
-    for (HostBuf *b : {&ctx->h_pkgs, &ctx->h_ppool, &ctx->h_gpool, &ctx->h_pairs, &ctx->h_events, &ctx->h_small,
-                 &ctx->h_ranges})
+    for (HostBuf *b : {&ctx->h_pkgs, &ctx->h_ppool, &ctx->h_gpool, &ctx->h_pairs, &ctx->h_events, &ctx->h_ranges})
         if (b->p) cudaFreeHost(b->p);
     for (auto &v : ctx->ev)
         if (v) cudaEventDestroy(v);
@@ -174,7 +172,7 @@ void r433b_destroy(r433b_ctx *ctx)
     for (auto &v : ctx->ev_t)
         if (v) cudaEventDestroy(v);
     if (ctx->ev_init) cudaEventDestroy(ctx->ev_init);
-    for (cudaStream_t st : {ctx->s_in, ctx->s_det, ctx->s_slc, ctx->s_out})
+    for (cudaStream_t st : {ctx->s_in, ctx->s_det, ctx->s_out})
         if (st) cudaStreamDestroy(st);
     delete ctx;
 }
@@ -357,13 +355,7 @@ int r433b_process(r433b_ctx *ctx, r433b_batch const *b)
     auto by_mod = [&](unsigned a, unsigned c) {
         // lanes of a warp should walk the same code: same slicer, then similar event cadence
         r433b_device const &x = ctx->devs[a], &y = ctx->devs[c];
-        static int const mode = getenv("R433B_SORT") ? atoi(getenv("R433B_SORT")) : 0; // tuning experiments only
-        if (mode == 1) { // event cadence first, slicer second
-            if (x.reset_limit != y.reset_limit) return x.reset_limit < y.reset_limit;
-            if (x.modulation != y.modulation) return x.modulation < y.modulation;
-            return a < c;
-        }
-        if (mode == 2) return a < c; // registration order
+        // (measured alternatives: event cadence first 61 ms, registration order 69 ms vs 35 ms)
         if (x.modulation != y.modulation) return x.modulation < y.modulation;
         if (x.reset_limit != y.reset_limit) return x.reset_limit < y.reset_limit;
         if (x.short_width != y.short_width) return x.short_width < y.short_width;

@@ -181,3 +181,43 @@ def test_cs8_input_is_cu8_plus_128(ctx, devices):
     for i, s in enumerate(streams):
         d = helpers.compare_results(o.run(s, 2), helpers.gpu_stream_results(ctx, i), f"cs8 {i}", stages=False)
         assert not d, "\n".join(d[:20])
+
+
+def test_fm_low_pass_override_and_wrapping_filter(ctx, devices):
+    """-Y filter values: a cutoff in Hz, one in us, and a ratio above 0.5 whose feedback coefficient
+    is negative -- the host can then no longer prove the int16 state never wraps, so the kernel
+    variant that is exact by induction alone (up to 31 bracket rounds) runs."""
+    streams = [synth.ook_stream(41, n_samples=1 << 19, n_bursts=4), synth.ook_stream(42, n_samples=1 << 19, n_bursts=4)]
+    try:
+        for lp in (25000.0, 12.0, 0.6):
+            ctx.set_fm_low_pass(lp)
+            gpu = run_gpu(ctx, streams, lib.FMT_CU8, 250000, 433920000)
+            o = oracle_for(devices)
+            o.set_fm_low_pass(lp)
+            for i, s in enumerate(streams):
+                check(gpu[i], o.run(s, 2), f"fm_low_pass {lp} stream {i}")
+    finally:
+        ctx.set_fm_low_pass(0.0)
+
+
+def test_priority_classes_stop_after_a_decode(ctx):
+    """run_ook_demods(): a priority class only runs while no earlier class decoded something
+    (src/r_api.c:444).  Same devices registered twice with priorities 0 and 5."""
+    table = {d["protocol_num"]: d for d in lib.default_device_table(include_disabled=True)}
+    devs = [dict(table[1]), dict(table[2], priority=5), dict(table[12]), dict(table[19], priority=10)]
+    x = synth.ook_stream(5, n_samples=1 << 18, n_bursts=2, kinds=("silvercrest",), decodable=True)
+    c = lib.Context(0)
+    try:
+        c.set_devices(devs)
+        c.process(x, np.array([0, x.nbytes], np.uint64), lib.FMT_CU8, 250000, 433920000)
+        c.fetch()
+        seen = []
+        c.dispatch(0, lambda pkg, dev, pd, bb: (seen.append((pkg, dev)), 1 if dev == 0 else 0)[1])
+        assert seen and {d for _, d in seen} <= {0, 2}      # classes 5 and 10 never ran
+        seen2 = []
+        c.dispatch(0, lambda pkg, dev, pd, bb: (seen2.append((pkg, dev)), 0)[1])
+        assert {d for _, d in seen2} == {0, 1, 2, 3}        # nobody decodes: every class runs
+        order = [d for p, d in seen2 if p == seen2[0][0]]
+        assert order == sorted(order, key=lambda d: (devs[d].get("priority", 0), d))
+    finally:
+        c.close()
