@@ -49,6 +49,7 @@ struct r433b_ctx {
     bool processed = false, fetched = false;
     unsigned fpdm = 0;
     int enable_fm = 0;
+    int lazy_fm = 1; // R433B_EAGER_FM=1 in the environment turns the on-demand FM path off (A/B checks)
     Levels lv{};
     // device memory (grow only)
     DevBuf d_data, d_offsets, d_train, d_pkgs, d_ppool, d_gpool, d_counters, d_am, d_fm;
@@ -150,6 +151,7 @@ int r433b_create(int cuda_device, r433b_ctx **out)
     for (auto &v : ctx->ev_t) cudaEventCreate(&v);
     cudaEventCreateWithFlags(&ctx->ev_init, cudaEventDisableTiming);
     ctx->lv = compute_levels(0, 0.0f, -12.1442f, 9.0f);
+    if (char const *v = getenv("R433B_EAGER_FM")) ctx->lazy_fm = !(v[0] && v[0] != '0');
     *out = ctx;
     return R433B_OK;
 }
@@ -307,6 +309,7 @@ int r433b_process(r433b_ctx *ctx, r433b_batch const *b)
     dp.flip = b->sample_format == R433B_FMT_CS8 ? 0x80808080u : 0u;
     dp.enable_fm = ctx->enable_fm;
     dp.fpdm = (int)ctx->fpdm;
+    dp.lazy_fm = ctx->lazy_fm;
     dp.rate = b->samp_rate;
     dp.block_samples = block_bytes / SS;
     dp.lv = ctx->lv;

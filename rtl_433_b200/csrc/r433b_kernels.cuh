@@ -22,6 +22,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <type_traits>
+
 #include "../../include/r433b.h"
 #include "r433b_core.cuh"
 #include "r433b_slice.cuh"
@@ -51,7 +53,8 @@ constexpr int kDetectCtasPerSm = 7;        // 28 warps per SM: 4096 streams are 
 // several time slices (so that copy-in of slice k+1 overlaps the kernels of slice k).
 struct StreamState {
     DetState d;
-    int y_am, y_fm, x_prev, xf_prev, pr_prev, pi_prev;
+    int y_am, y_fm, x_prev, xf_prev;
+    unsigned fm_tile; // index of the tile for which (y_fm, xf_prev) are the FM low-pass carry-in
     unsigned seq;
     int flushed;
 };
@@ -66,6 +69,7 @@ struct DetectParams {
     int first_chunk;              // start from reset_sdr_flow() state instead of the saved one
     struct StreamState *state;    // per-stream carried state between launches of one batch
     int use_mag, enable_fm, fpdm;
+    int lazy_fm; // compute discriminator + FM low-pass only for tiles the detector reads them in
     unsigned flip; // XOR mask applied to every loaded word: 0x80808080 turns cs8 into cu8
     unsigned rate, block_samples;
     Levels lv;
@@ -107,6 +111,243 @@ struct TileCfg {
     static constexpr int kTileWords = 32 * (W * C + 1);
 };
 
+// 16 contiguous bytes (8 cu8 / 4 cs16 samples) of tile tt for this lane: one fully coalesced
+// 128-bit load per lane; zero-filled past the nvt valid samples of the tile.
+template <int SS>
+__device__ __forceinline__ void load_group(uint8_t const *src, unsigned long long tt, int n0, int nvt, unsigned flip,
+        uint32_t (&rw)[4])
+{
+    constexpr int SPL = 16 / SS;
+    rw[0] = rw[1] = rw[2] = rw[3] = 0u;
+    uint8_t const *g = src + (tt + (unsigned long long)n0) * SS;
+    if (n0 + SPL <= nvt) {
+        uint4 v = __ldg(reinterpret_cast<uint4 const *>(g));
+        rw[0] = v.x ^ flip;
+        rw[1] = v.y ^ flip;
+        rw[2] = v.z ^ flip;
+        rw[3] = v.w ^ flip;
+    } else if (n0 < nvt) { // ragged end of the stream
+        int nb = (nvt - n0) * SS;
+        for (int bidx = 0; bidx < nb; ++bidx) rw[bidx >> 2] |= (uint32_t)(g[bidx] ^ (flip & 0xff)) << (8 * (bidx & 3));
+    }
+}
+
+// ------------------------------------------------------------------- FM on demand ------
+//
+// The discriminator and its low-pass are only looked at inside packages, so k_detect computes
+// them per tile when the detector first asks.  fm_make() is deliberately NOT inlined: it is the
+// cold side of the tile loop and keeps its own register allocation.
+//
+// fm_tile(tt): discriminator of tile tt (IQ re-read from global memory: L1/L2 hits for the
+// current tile) into the high halves / second words of the shared-memory tile, then the FM
+// low-pass by bracket rounds.  For the CURRENT tile every lane needs its exact start state and a
+// final pass writes FM next to AM.  For an EARLIER tile only the state at its end matters: rounds
+// stop as soon as lane 31's end bracket has collapsed.  `unknown` starts lane 0 from the full
+// range too (its first sample only provides x[n-1]).
+//
+// If the filter state is stale (tiles were skipped) it is rebuilt from the previous tile alone:
+// from ANY start state the brackets collapse within a few dozen samples of a live signal.  If they
+// do not (a constant discriminator output parks the two ends on different fixed points of the
+// floor map), walk forward from the last exact state instead.
+struct FmCarry {
+    int y, xf; // filter state and discriminator output after the last sample of the tile
+};
+
+template <int SS, bool NOWRAP>
+__device__ __forceinline__ FmCarry fm_make(uint8_t const *src, uint32_t *tile, unsigned long long t0, int nv_tile,
+        unsigned long long fm_at, int y_fm, int xf_prev, unsigned flip, long long fa1, long long fb0)
+{
+    using Cfg = TileCfg<SS>;
+    constexpr int C = Cfg::C;
+    constexpr int T = Cfg::T;
+    constexpr int W = Cfg::W;
+    constexpr int SPL = 16 / SS;
+    constexpr int NQ = T / (32 * SPL);
+    int const lane = threadIdx.x & 31;
+    uint32_t *mine = tile + lane * (W * C + 1);
+    auto step16 = [](int y, int ca, int cb, int xsum) { return NOWRAP ? iir16_nowrap(y, ca, cb, xsum) : iir16(y, ca, cb, xsum); };
+
+    auto fm_tile = [&](unsigned long long tt, int nvt, bool current, bool unknown, int &cy, int &cf) -> bool {
+        int pri = 0, prq = 0; // IQ in front of lane 0's group
+        if (tt > 0) {
+            uint8_t const *g = src + (tt - 1) * SS;
+            if (SS == 2) {
+                pri = (int)(g[0] ^ (flip & 0xff)) - 128;
+                prq = (int)(g[1] ^ (flip & 0xff)) - 128;
+            } else {
+                uint32_t w = *reinterpret_cast<uint32_t const *>(g);
+                pri = (int)(int16_t)(w & 0xffff);
+                prq = (int)(int16_t)(w >> 16);
+            }
+        }
+#pragma unroll 1
+        for (int q = 0; q < NQ; ++q) {
+            int const n0 = q * 32 * SPL + lane * SPL;
+            uint32_t rw[4];
+            load_group<SS>(src, tt, n0, nvt, flip, rw);
+            int li, lq; // last sample of this lane's group, for the lane to the right
+            if (SS == 2) {
+                li = (int)((rw[3] >> 16) & 0xff) - 128;
+                lq = (int)((rw[3] >> 24) & 0xff) - 128;
+            } else {
+                li = (int)(int16_t)(rw[3] & 0xffff);
+                lq = (int)(int16_t)(rw[3] >> 16);
+            }
+            int pi_ = __shfl_up_sync(0xffffffffu, li, 1);
+            int pq_ = __shfl_up_sync(0xffffffffu, lq, 1);
+            if (lane == 0) {
+                pi_ = pri;
+                pq_ = prq;
+            }
+            pri = __shfl_sync(0xffffffffu, li, 31);
+            prq = __shfl_sync(0xffffffffu, lq, 31);
+#pragma unroll
+            for (int j = 0; j < SPL; ++j) {
+                int ci, cq, xf;
+                if (SS == 2) {
+                    uint32_t w = rw[j >> 1];
+                    ci = (int)((w >> ((j & 1) * 16)) & 0xff) - 128;
+                    cq = (int)((w >> ((j & 1) * 16 + 8)) & 0xff) - 128;
+                    xf = atan16(cq * pi_ - ci * pq_, ci * pi_ + cq * pq_);
+                } else {
+                    uint32_t w = rw[j];
+                    ci = (int)(int16_t)(w & 0xffff);
+                    cq = (int)(int16_t)(w >> 16);
+                    long long re = (long long)ci * pi_ + (long long)cq * pq_;
+                    long long im = (long long)cq * pi_ - (long long)ci * pq_;
+                    xf = atan32((int)(unsigned)(unsigned long long)im, (int)(unsigned)(unsigned long long)re);
+                }
+                pi_ = ci;
+                pq_ = cq;
+                int at = word_index<C, W>(n0 + j);
+                if (W == 1)
+                    reinterpret_cast<uint16_t *>(tile)[2 * at + 1] = (uint16_t)xf;
+                else
+                    tile[at + 1] = (uint32_t)xf;
+            }
+        }
+        __syncwarp();
+
+        auto xf_at = [&](uint32_t const *w) { return W == 1 ? (int)(int16_t)(w[0] >> 16) : (int)w[1]; };
+        int nvl = nvt - lane * C;
+        nvl = nvl < 0 ? 0 : (nvl > C ? C : nvl);
+        int kb = 0;
+        int fl; // discriminator output of the sample in front of the chunk
+        if (lane == 0) {
+            fl = cf;
+            if (unknown) {
+                kb = 1;
+                fl = xf_at(mine);
+            }
+        } else {
+            fl = xf_at(mine - 1 - W);
+        }
+        int lo_f, hi_f;
+        if (lane == 0 && !unknown) {
+            lo_f = hi_f = cy;
+        } else {
+            lo_f = SS == 2 ? -32768 : (int)0x80000000;
+            hi_f = SS == 2 ? 32767 : 0x7fffffff;
+        }
+        bool ok = false;
+        int yend = 0;
+#pragma unroll 1
+        for (int round = 0; round < 32; ++round) {
+            if (current) {
+                // lanes 0..round are exact by induction even if the filter could wrap
+                bool trust = NOWRAP ? (lo_f == hi_f) : (lane <= round);
+                if (__all_sync(0xffffffffu, trust)) {
+                    ok = true;
+                    break;
+                }
+            }
+            int e0 = lo_f, e1 = hi_f;
+            int fp = fl;
+R4_UNROLL(R4_UNROLL_IIR)
+            for (int k = kb; k < nvl; ++k) {
+                int v = xf_at(mine + k * W);
+                if (SS == 2) {
+                    int fsum = v + fp;
+                    e0 = step16(e0, (int)fa1, (int)fb0, fsum);
+                    e1 = step16(e1, (int)fa1, (int)fb0, fsum);
+                } else {
+                    long long fsum = (long long)v + fp;
+                    e0 = iir32(e0, fa1, fb0, fsum);
+                    e1 = iir32(e1, fa1, fb0, fsum);
+                }
+                fp = v;
+            }
+            if (!current) {
+                int z0 = __shfl_sync(0xffffffffu, e0, 31);
+                int z1 = __shfl_sync(0xffffffffu, e1, 31);
+                if (z0 == z1) {
+                    yend = z0;
+                    ok = true;
+                    break;
+                }
+            }
+            int n0 = __shfl_up_sync(0xffffffffu, e0, 1);
+            int n1 = __shfl_up_sync(0xffffffffu, e1, 1);
+            if (lane != 0) {
+                lo_f = n0;
+                hi_f = n1;
+            }
+        }
+        if (!current) {
+            if (ok) {
+                cy = yend;
+                cf = xf_at(tile + 31 * (W * C + 1) + (C - 1) * W);
+            }
+            __syncwarp();
+            return ok;
+        }
+        // final pass of the current tile: FM next to AM
+        int yf = lo_f;
+        int fp = fl;
+R4_UNROLL(R4_UNROLL_IIR)
+        for (int k = 0; k < nvl; ++k) {
+            int v = xf_at(mine + k * W);
+            int fo;
+            if (SS == 2) {
+                yf = step16(yf, (int)fa1, (int)fb0, v + fp);
+                fo = yf;
+            } else {
+                yf = iir32(yf, fa1, fb0, (long long)v + fp);
+                fo = yf >> 16;
+            }
+            fp = v;
+            reinterpret_cast<uint16_t *>(mine)[2 * k * W + 1] = (uint16_t)(int16_t)fo;
+        }
+        int last_lane = (nvt - 1) / C;
+        cy = __shfl_sync(0xffffffffu, yf, last_lane);
+        cf = __shfl_sync(0xffffffffu, fp, last_lane);
+        __syncwarp();
+        return true;
+    };
+
+    int cy = y_fm, cf = xf_prev;
+    unsigned long long tt = fm_at == t0 ? t0 : t0 - T;
+    bool unknown = tt != fm_at;
+    for (;;) {
+        bool const current = tt == t0;
+        bool ok = fm_tile(tt, current ? nv_tile : T, current, unknown, cy, cf);
+        if (!ok) {
+            cy = y_fm;
+            cf = xf_prev;
+            tt = fm_at;
+            unknown = false;
+            continue;
+        }
+        unknown = false;
+        if (current) break;
+        tt += T;
+    }
+    FmCarry r;
+    r.y = cy;
+    r.xf = cf;
+    return r;
+}
+
 template <int SS, bool NOWRAP>
 __global__ void __launch_bounds__(kDetectWarps * 32, kDetectCtasPerSm) k_detect(DetectParams p)
 {
@@ -122,12 +363,12 @@ __global__ void __launch_bounds__(kDetectWarps * 32, kDetectCtasPerSm) k_detect(
     if (s >= p.stream_end) return;
 
     uint32_t *tile = smem + warp * Cfg::kTileWords;
+    __shared__ DetState s_park[kDetectWarps];
+    DetState *park = &s_park[warp];
     bool const fm_on = p.enable_fm != 0;
 
     unsigned long long const byte0 = p.offsets[s];
     unsigned long long const N = (p.lengths ? p.lengths[s] : p.offsets[s + 1] - byte0) / SS;
-    uint8_t const *src = p.data + byte0;
-    unsigned long long const sample0 = byte0 / SS;
 
     Trains tr;
     tr.ook_pulse = p.train_scratch + (size_t)s * kTrainInts;
@@ -142,13 +383,12 @@ __global__ void __launch_bounds__(kDetectWarps * 32, kDetectCtasPerSm) k_detect(
     DetState d;
     unsigned seq = 0;
     int const per_ms = (int)(p.rate / 1000);
-    unsigned long long const n_blocks = (N + p.block_samples - 1) / p.block_samples;
 
     // carried filter / demod state (reset_sdr_flow(): all zero)
     int y_am = 0, y_fm = 0;
     int x_prev = 0;          // raw envelope of the previous sample
-    int xf_prev = 0;         // previous discriminator output
-    int pr_prev = 0, pi_prev = 0; // previous IQ sample (offset removed)
+    int xf_prev = 0;         // discriminator output of the sample in front of tile `fm_at`
+    unsigned fm_tile = 0;    // index of the tile for which (y_fm, xf_prev) are the exact carry-in
     int flushed = 0;
     if (p.first_chunk) {
         det_reset(d);
@@ -160,12 +400,14 @@ __global__ void __launch_bounds__(kDetectWarps * 32, kDetectCtasPerSm) k_detect(
         y_fm = ss.y_fm;
         x_prev = ss.x_prev;
         xf_prev = ss.xf_prev;
-        pr_prev = ss.pr_prev;
-        pi_prev = ss.pi_prev;
+        fm_tile = ss.fm_tile;
         seq = ss.seq;
         flushed = ss.flushed;
     }
-    unsigned long long const t_end = p.sample_end < N ? p.sample_end : N;
+    // The discriminator and its low-pass are only looked at inside packages (PULSE, and GAP_START
+    // of the first pulse: src/pulse_detect.c:362-365, :367-383).  With a filter that cannot wrap
+    // they are therefore computed per tile ON DEMAND; see make_fm below.
+    bool const lazy_fm = NOWRAP && fm_on && p.lazy_fm && !p.am_out;
 
     auto emit = [&](int type, unsigned long long pos, bool flush) {
         PackageHeader h = package_header(d, type);
@@ -189,7 +431,7 @@ __global__ void __launch_bounds__(kDetectWarps * 32, kDetectCtasPerSm) k_detect(
                 p.gap_pool[off + i] = sg[i];
             }
             if (lane == 0) {
-                unsigned long long blk = flush ? n_blocks : pos / p.block_samples;
+                unsigned long long blk = flush ? (N + p.block_samples - 1) / p.block_samples : pos / p.block_samples;
                 unsigned long long bstart = blk * p.block_samples;
                 unsigned long long blen = flush ? 0 : (N - bstart < p.block_samples ? N - bstart : p.block_samples);
                 r433b_package k;
@@ -215,170 +457,177 @@ __global__ void __launch_bounds__(kDetectWarps * 32, kDetectCtasPerSm) k_detect(
         seq++;
     };
 
-    for (unsigned long long t0 = p.sample_begin; t0 < t_end; t0 += T) {
+    for (unsigned long long t0 = p.sample_begin; t0 < p.sample_end && t0 < N; t0 += T) {
+        uint8_t const *src = p.data + p.offsets[s]; // re-derived per tile: not worth two registers across the walk
         unsigned long long const remain = N - t0;
         int const nv_tile = remain < (unsigned long long)T ? (int)remain : T;
         int nv = nv_tile - lane * C; // valid samples in this lane's chunk
         nv = nv < 0 ? 0 : (nv > C ? C : nv);
 
-        // ---- phase 1: sample maps, coalesced ------------------------------------------------
-        // Iteration q: lane l takes the 16 contiguous bytes (8 cu8 / 4 cs16 samples) at
-        // q*512 + l*16 of the tile: one fully coalesced 128-bit load per lane.  Envelope x and
-        // phase-discriminator xf go to the warp's shared-memory tile.
+        // ---- the tile front: sample maps + exact low-pass(es) --------------------------------
+        // Two instances of the same code.  front(true): envelope AND discriminator, both filters
+        // in the same loops (four independent dependency chains per lane) -- used while a package
+        // is open (and always when FM cannot be deferred).  front(false): envelope and AM filter
+        // only -- used while the detector is IDLE; if a package starts inside such a tile,
+        // fm_make() supplies FM for it afterwards.
         constexpr int SPL = 16 / SS;          // samples per 128-bit load
         constexpr int NQ = T / (32 * SPL);    // load iterations per tile (4)
-#pragma unroll 1
-        for (int q = 0; q < NQ; ++q) {
-            int const n0 = q * 32 * SPL + lane * SPL;
-            uint32_t rw[4] = {0u, 0u, 0u, 0u};
-            uint8_t const *g = src + (t0 + (unsigned long long)n0) * SS;
-            if (n0 + SPL <= nv_tile) {
-                uint4 v = __ldg(reinterpret_cast<uint4 const *>(g));
-                rw[0] = v.x ^ p.flip;
-                rw[1] = v.y ^ p.flip;
-                rw[2] = v.z ^ p.flip;
-                rw[3] = v.w ^ p.flip;
-            } else if (n0 < nv_tile) { // ragged end of the stream
-                int nb = (nv_tile - n0) * SS;
-                for (int bidx = 0; bidx < nb; ++bidx) rw[bidx >> 2] |= (uint32_t)(g[bidx] ^ (p.flip & 0xff)) << (8 * (bidx & 3));
-            }
-            int li, lq; // last sample of this lane's group, for the lane to the right
-            if (SS == 2) {
-                li = (int)((rw[3] >> 16) & 0xff) - 128;
-                lq = (int)((rw[3] >> 24) & 0xff) - 128;
-            } else {
-                li = (int)(int16_t)(rw[3] & 0xffff);
-                lq = (int)(int16_t)(rw[3] >> 16);
-            }
-            int pi_ = __shfl_up_sync(0xffffffffu, li, 1);
-            int pq_ = __shfl_up_sync(0xffffffffu, lq, 1);
-            if (lane == 0) {
-                pi_ = pr_prev;
-                pq_ = pi_prev;
-            }
-            pr_prev = __shfl_sync(0xffffffffu, li, 31);
-            pi_prev = __shfl_sync(0xffffffffu, lq, 31);
-#pragma unroll
-            for (int j = 0; j < SPL; ++j) {
-                int ci, cq, x, xf;
-                if (SS == 2) {
-                    uint32_t w = rw[j >> 1];
-                    int ri = (int)((w >> ((j & 1) * 16)) & 0xff);
-                    int rq = (int)((w >> ((j & 1) * 16 + 8)) & 0xff);
-                    ci = ri - 128;
-                    cq = rq - 128;
-                    x = p.use_mag ? mag_cu8(ri, rq) : env_cu8(ri, rq);
-                } else {
-                    uint32_t w = rw[j];
-                    ci = (int)(int16_t)(w & 0xffff);
-                    cq = (int)(int16_t)(w >> 16);
-                    x = mag_cs16(ci, cq);
-                }
-                if (fm_on) {
-                    if (SS == 2) {
-                        xf = atan16(cq * pi_ - ci * pq_, ci * pi_ + cq * pq_);
-                    } else {
-                        long long re = (long long)ci * pi_ + (long long)cq * pq_;
-                        long long im = (long long)cq * pi_ - (long long)ci * pq_;
-                        xf = atan32((int)(unsigned)(unsigned long long)im, (int)(unsigned)(unsigned long long)re);
-                    }
-                } else {
-                    xf = (int)(int16_t)x; // buf.fm aliases the raw envelope when FM is off
-                }
-                pi_ = ci;
-                pq_ = cq;
-                int at = word_index<C, W>(n0 + j);
-                if (W == 1) {
-                    tile[at] = (uint32_t)x | ((uint32_t)xf << 16);
-                } else {
-                    tile[at] = (uint32_t)x;
-                    tile[at + 1] = (uint32_t)xf;
-                }
-            }
-        }
-        __syncwarp();
-
-        // ---- phase 2: the two IIR low-passes, exact and lane-parallel -----------------------
-        // lane l owns samples [l*C, l*C + C) of the tile; nv of them exist
-        uint32_t *mine = tile + lane * (W * C + 1);
-        int xl, fl; // envelope / discriminator of the sample in front of the chunk
-        if (lane == 0) {
-            // the reference keeps x[-1] as int16 across block calls (src/baseband.c:167)
-            xl = (t0 % p.block_samples == 0) ? (int)(int16_t)x_prev : x_prev;
-            fl = xf_prev;
-        } else {
-            uint32_t const *left = mine - 1 - W; // last sample of the lane to the left
-            xl = (int)(left[0] & 0xffff);
-            fl = W == 1 ? (int)(int16_t)(left[0] >> 16) : (int)left[1];
-        }
-        int const a1 = p.lpf_a1, b0 = p.lpf_b0;
-        long long const fa1 = p.fm_a1, fb0 = p.fm_b0;
+        uint32_t *mine = tile + lane * (W * C + 1); // lane l owns samples [l*C, l*C + C) of the tile; nv of them exist
         auto step16 = [](int y, int ca, int cb, int xsum) { return NOWRAP ? iir16_nowrap(y, ca, cb, xsum) : iir16(y, ca, cb, xsum); };
-
-        // both ends of both brackets advance together: four independent dependency chains
-        auto run_chunk2 = [&](int &ya0, int &ya1, int &yf0, int &yf1) {
-            int xp = xl, fp = fl;
-R4_UNROLL(R4_UNROLL_IIR)
-            for (int k = 0; k < nv; ++k) {
-                uint32_t w0 = mine[k * W];
-                int x = (int)(w0 & 0xffff);
-                int xsum = x + xp;
-                ya0 = step16(ya0, a1, b0, xsum);
-                ya1 = step16(ya1, a1, b0, xsum);
-                xp = x;
-                if (fm_on) {
+        auto front = [&](auto with_fm) {
+            constexpr bool FM = decltype(with_fm)::value;
+            // phase 1: maps, coalesced.  Iteration q: lane l takes the 16 contiguous bytes (8 cu8 /
+            // 4 cs16 samples) at q*512 + l*16 of the tile: one 128-bit load per lane.
+            int pri = 0, prq = 0; // IQ in front of lane 0's group
+            if (FM && t0 > 0) {
+                uint8_t const *g = src + (t0 - 1) * SS;
+                if (SS == 2) {
+                    pri = (int)(g[0] ^ (p.flip & 0xff)) - 128;
+                    prq = (int)(g[1] ^ (p.flip & 0xff)) - 128;
+                } else {
+                    uint32_t w = *reinterpret_cast<uint32_t const *>(g);
+                    pri = (int)(int16_t)(w & 0xffff);
+                    prq = (int)(int16_t)(w >> 16);
+                }
+            }
+#pragma unroll 1
+            for (int q = 0; q < NQ; ++q) {
+                int const n0 = q * 32 * SPL + lane * SPL;
+                uint32_t rw[4];
+                load_group<SS>(src, t0, n0, nv_tile, p.flip, rw);
+                int pi_ = 0, pq_ = 0;
+                if (FM) {
+                    int li, lq; // last sample of this lane's group, for the lane to the right
                     if (SS == 2) {
-                        int v = (int)(int16_t)(w0 >> 16);
-                        int fsum = v + fp;
-                        yf0 = step16(yf0, (int)fa1, (int)fb0, fsum);
-                        yf1 = step16(yf1, (int)fa1, (int)fb0, fsum);
-                        fp = v;
+                        li = (int)((rw[3] >> 16) & 0xff) - 128;
+                        lq = (int)((rw[3] >> 24) & 0xff) - 128;
                     } else {
-                        int v = (int)mine[k * W + 1];
-                        long long fsum = (long long)v + fp;
-                        yf0 = iir32(yf0, fa1, fb0, fsum);
-                        yf1 = iir32(yf1, fa1, fb0, fsum);
-                        fp = v;
+                        li = (int)(int16_t)(rw[3] & 0xffff);
+                        lq = (int)(int16_t)(rw[3] >> 16);
+                    }
+                    pi_ = __shfl_up_sync(0xffffffffu, li, 1);
+                    pq_ = __shfl_up_sync(0xffffffffu, lq, 1);
+                    if (lane == 0) {
+                        pi_ = pri;
+                        pq_ = prq;
+                    }
+                    pri = __shfl_sync(0xffffffffu, li, 31);
+                    prq = __shfl_sync(0xffffffffu, lq, 31);
+                }
+#pragma unroll
+                for (int j = 0; j < SPL; ++j) {
+                    int ci, cq, x, xf = 0;
+                    if (SS == 2) {
+                        uint32_t w = rw[j >> 1];
+                        int ri = (int)((w >> ((j & 1) * 16)) & 0xff);
+                        int rq = (int)((w >> ((j & 1) * 16 + 8)) & 0xff);
+                        ci = ri - 128;
+                        cq = rq - 128;
+                        x = p.use_mag ? mag_cu8(ri, rq) : env_cu8(ri, rq);
+                    } else {
+                        uint32_t w = rw[j];
+                        ci = (int)(int16_t)(w & 0xffff);
+                        cq = (int)(int16_t)(w >> 16);
+                        x = mag_cs16(ci, cq);
+                    }
+                    if (FM) {
+                        if (SS == 2) {
+                            xf = atan16(cq * pi_ - ci * pq_, ci * pi_ + cq * pq_);
+                        } else {
+                            long long re = (long long)ci * pi_ + (long long)cq * pq_;
+                            long long im = (long long)cq * pi_ - (long long)ci * pq_;
+                            xf = atan32((int)(unsigned)(unsigned long long)im, (int)(unsigned)(unsigned long long)re);
+                        }
+                        pi_ = ci;
+                        pq_ = cq;
+                    }
+                    int at = word_index<C, W>(n0 + j);
+                    if (W == 1) {
+                        tile[at] = (uint32_t)x | ((uint32_t)xf << 16);
+                    } else {
+                        tile[at] = (uint32_t)x;
+                        if (FM) tile[at + 1] = (uint32_t)xf;
                     }
                 }
             }
-        };
+            __syncwarp();
 
-        int lo_a, hi_a, lo_f, hi_f;
-        if (lane == 0) {
-            lo_a = hi_a = y_am;
-            lo_f = hi_f = y_fm;
-        } else {
-            lo_a = -32768;
-            hi_a = 32767;
-            lo_f = SS == 2 ? -32768 : (int)0x80000000;
-            hi_f = SS == 2 ? 32767 : 0x7fffffff;
-        }
-#pragma unroll 1
-        for (int round = 0; round < 31; ++round) {
-            bool mine_ok = (lo_a == hi_a) && (!fm_on || lo_f == hi_f);
-            // lanes 0..round are exact by induction even if the filter could wrap
-            bool trust = NOWRAP ? mine_ok : (lane <= round);
-            if (__all_sync(0xffffffffu, trust)) break;
-            int ea_lo = lo_a, ea_hi = hi_a, ef_lo = lo_f, ef_hi = hi_f;
-            run_chunk2(ea_lo, ea_hi, ef_lo, ef_hi);
-            int na_lo = __shfl_up_sync(0xffffffffu, ea_lo, 1);
-            int na_hi = __shfl_up_sync(0xffffffffu, ea_hi, 1);
-            int nf_lo = __shfl_up_sync(0xffffffffu, ef_lo, 1);
-            int nf_hi = __shfl_up_sync(0xffffffffu, ef_hi, 1);
-            if (lane != 0) {
-                lo_a = na_lo;
-                hi_a = na_hi;
-                lo_f = nf_lo;
-                hi_f = nf_hi;
+            // phase 2: the low-pass(es), exact and lane-parallel
+            int xl, fl = 0; // envelope / discriminator of the sample in front of the chunk
+            if (lane == 0) {
+                // the reference keeps x[-1] as int16 across block calls (src/baseband.c:167)
+                xl = (t0 % p.block_samples == 0) ? (int)(int16_t)x_prev : x_prev;
+                fl = xf_prev;
+            } else {
+                uint32_t const *left = mine - 1 - W; // last sample of the lane to the left
+                xl = (int)(left[0] & 0xffff);
+                if (FM) fl = W == 1 ? (int)(int16_t)(left[0] >> 16) : (int)left[1];
             }
-        }
+            int const a1 = p.lpf_a1, b0 = p.lpf_b0;
+            long long const fa1 = p.fm_a1, fb0 = p.fm_b0;
+            int lo_a, hi_a, lo_f, hi_f;
+            if (lane == 0) {
+                lo_a = hi_a = y_am;
+                lo_f = hi_f = y_fm;
+            } else {
+                lo_a = -32768;
+                hi_a = 32767;
+                lo_f = SS == 2 ? -32768 : (int)0x80000000;
+                hi_f = SS == 2 ? 32767 : 0x7fffffff;
+            }
+#pragma unroll 1
+            for (int round = 0; round < 31; ++round) {
+                bool mine_ok = (lo_a == hi_a) && (!FM || lo_f == hi_f);
+                // lanes 0..round are exact by induction even if the filter could wrap
+                bool trust = NOWRAP ? mine_ok : (lane <= round);
+                if (__all_sync(0xffffffffu, trust)) break;
+                // both ends of every bracket advance together: independent dependency chains
+                int ea_lo = lo_a, ea_hi = hi_a, ef_lo = lo_f, ef_hi = hi_f;
+                int xp = xl, fp = fl;
+R4_UNROLL(R4_UNROLL_IIR)
+                for (int k = 0; k < nv; ++k) {
+                    uint32_t w0 = mine[k * W];
+                    int x = (int)(w0 & 0xffff);
+                    int xsum = x + xp;
+                    ea_lo = step16(ea_lo, a1, b0, xsum);
+                    ea_hi = step16(ea_hi, a1, b0, xsum);
+                    xp = x;
+                    if (FM) {
+                        if (SS == 2) {
+                            int v = (int)(int16_t)(w0 >> 16);
+                            int fsum = v + fp;
+                            ef_lo = step16(ef_lo, (int)fa1, (int)fb0, fsum);
+                            ef_hi = step16(ef_hi, (int)fa1, (int)fb0, fsum);
+                            fp = v;
+                        } else {
+                            int v = (int)mine[k * W + 1];
+                            long long fsum = (long long)v + fp;
+                            ef_lo = iir32(ef_lo, fa1, fb0, fsum);
+                            ef_hi = iir32(ef_hi, fa1, fb0, fsum);
+                            fp = v;
+                        }
+                    }
+                }
+                int na_lo = __shfl_up_sync(0xffffffffu, ea_lo, 1);
+                int na_hi = __shfl_up_sync(0xffffffffu, ea_hi, 1);
+                if (lane != 0) {
+                    lo_a = na_lo;
+                    hi_a = na_hi;
+                }
+                if (FM) {
+                    int nf_lo = __shfl_up_sync(0xffffffffu, ef_lo, 1);
+                    int nf_hi = __shfl_up_sync(0xffffffffu, ef_hi, 1);
+                    if (lane != 0) {
+                        lo_f = nf_lo;
+                        hi_f = nf_hi;
+                    }
+                }
+            }
 
-        // ---- phase 3: final pass from the exact state; AM|FM replace x|xf in place -----------
-        {
+            // phase 3: final pass from the exact state; AM|FM replace x|xf in place
             int ya = lo_a, yf = lo_f;
             int xp = xl, fp = fl;
-            unsigned long long const gbase = sample0 + t0 + (unsigned long long)lane * C;
+            unsigned long long const gbase = p.am_out ? p.offsets[s] / SS + t0 + (unsigned long long)lane * C : 0;
 R4_UNROLL(R4_UNROLL_IIR)
             for (int k = 0; k < nv; ++k) {
                 uint32_t w0 = mine[k * W];
@@ -386,7 +635,7 @@ R4_UNROLL(R4_UNROLL_IIR)
                 ya = step16(ya, a1, b0, x + xp);
                 xp = x;
                 int fo;
-                if (fm_on) {
+                if (FM) {
                     if (SS == 2) {
                         int v = (int)(int16_t)(w0 >> 16);
                         yf = step16(yf, (int)fa1, (int)fb0, v + fp);
@@ -399,7 +648,7 @@ R4_UNROLL(R4_UNROLL_IIR)
                         fo = yf >> 16;
                     }
                 } else {
-                    fo = (int)(int16_t)x;
+                    fo = fm_on ? 0 : (int)(int16_t)x; // buf.fm aliases the raw envelope when FM is off
                 }
                 mine[k * W] = (uint32_t)(uint16_t)(int16_t)ya | ((uint32_t)(uint16_t)(int16_t)fo << 16);
                 if (p.am_out) {
@@ -410,11 +659,27 @@ R4_UNROLL(R4_UNROLL_IIR)
             // carries for the next tile: the state after the last valid sample
             int last_lane = (nv_tile - 1) / C;
             y_am = __shfl_sync(0xffffffffu, ya, last_lane);
-            y_fm = __shfl_sync(0xffffffffu, yf, last_lane);
             x_prev = __shfl_sync(0xffffffffu, xp, last_lane);
-            xf_prev = __shfl_sync(0xffffffffu, fp, last_lane);
-        }
+            if (FM) {
+                y_fm = __shfl_sync(0xffffffffu, yf, last_lane);
+                xf_prev = __shfl_sync(0xffffffffu, fp, last_lane);
+                fm_tile = (unsigned)(t0 / T) + 1;
+            }
+        };
+        // d.st != IDLE at a tile start implies FM was made for the previous tile
+        bool const fused = fm_on && (!lazy_fm || (d.st != kIdle && fm_tile == (unsigned)(t0 / T)));
+        // The (warp-uniform) detector state is not needed by the front: park it in shared memory
+        // so that the filter loops have the registers (otherwise ptxas spills inside them).
+        if (lane == 0) *park = d;
         __syncwarp();
+        if (fused)
+            front(std::true_type{});
+        else
+            front(std::false_type{});
+        __syncwarp();
+        d = *park;
+
+        bool fm_ready = !fm_on || fused;
 
         // ---- package detector over the tile (warp-uniform) -------------------------------
         if (t0 % p.block_samples == 0) det_call_boundary(d, p.lv);
@@ -678,7 +943,12 @@ R4_UNROLL(R4_UNROLL_PULSE)
             return cnt;
         };
 
-        for (int n = 0; n < nv_tile;) {
+        // The detector walks the tile until it is done or first needs FM; in that case FM is made
+        // out here (not inside the walk: the walk keeps its registers) and the walk resumes.
+        int n = 0;
+        for (;;) {
+        for (; n < nv_tile;) {
+            if (!fm_ready && (d.st == kPulse || (d.st == kGapStart && d.ook_n == 0))) break;
             int adv = 0;
             if (d.st == kIdle) {
                 adv = idle_tile(n);
@@ -705,6 +975,19 @@ R4_UNROLL(R4_UNROLL_PULSE)
             }
             ++n;
         }
+        if (n >= nv_tile) break;
+        {
+            if (lane == 0) *park = d;
+            __syncwarp();
+            FmCarry c = fm_make<SS, NOWRAP>(src, tile, t0, nv_tile, (unsigned long long)fm_tile * T, y_fm, xf_prev, p.flip,
+                    p.fm_a1, p.fm_b0);
+            y_fm = c.y;
+            xf_prev = c.xf;
+            fm_tile = (unsigned)(t0 / T) + 1;
+            fm_ready = true;
+            d = *park;
+        }
+        } // walk / make FM / resume
         __syncwarp();
     }
 
@@ -724,8 +1007,7 @@ R4_UNROLL(R4_UNROLL_PULSE)
         ss.y_fm = y_fm;
         ss.x_prev = x_prev;
         ss.xf_prev = xf_prev;
-        ss.pr_prev = pr_prev;
-        ss.pi_prev = pi_prev;
+        ss.fm_tile = fm_tile;
         ss.seq = seq;
         ss.flushed = flushed;
     }
