@@ -38,11 +38,18 @@ def run_gpu(ctx, streams, fmt, rate, freq, fpdm=lib.FPDM_AUTO, block_bytes=0):
     assert lens == padded
     offsets = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
     data = np.concatenate([s.view(np.uint8).ravel() for s in streams]) if streams else np.zeros(0, np.uint8)
+    # Without the stage dump the kernel computes FM on demand (only inside packages, filter state
+    # rebuilt from the previous tile); with it, FM is computed for every tile.  Both must agree.
+    ctx.process(data, offsets, fmt, rate, freq, fpdm, block_bytes, want_stages=False)
+    ctx.fetch()
+    on_demand = [helpers.gpu_stream_results(ctx, i) for i in range(len(streams))]
     ctx.process(data, offsets, fmt, rate, freq, fpdm, block_bytes, want_stages=True)
     ctx.fetch()
     out = []
     for i, s in enumerate(streams):
         r = helpers.gpu_stream_results(ctx, i)
+        d = helpers.compare_results(r, on_demand[i], f"FM on demand vs every tile, stream {i}", stages=False)
+        assert not d, "\n".join(d[:20])
         n = lens[i] // fmt
         r["am"], r["fm"] = ctx.copy_stage(i, n)
         out.append(r)
@@ -102,6 +109,37 @@ def test_silence_and_reference_vectors(ctx, devices):
     bb = [e["bitbuffer"] for e in r["events"] if e["dev"] == 0][0]
     assert int(bb["num_rows"]) == 4
     assert [refh.row_hex(bb, k) for k in range(4)] == ["{33}7c2600020"] * 4
+
+
+def test_fm_rebuild_after_constant_input(ctx, devices):
+    """FM is computed on demand and its filter state rebuilt from the tile in front of a package.
+    Over exactly constant input (digital silence between signals) the rebuild cannot converge --
+    the two bracket ends sit on different fixed points of the floor map -- and the kernel has to
+    walk forward from the last exact state instead.  cu8 and cs16, silence in front and in the
+    middle, through run_gpu's on-demand / every-tile comparison and against the oracle."""
+    a, b = synth.ook_stream(51, n_samples=1 << 18, n_bursts=3), synth.ook_stream(52, n_samples=1 << 18, n_bursts=3)
+    quiet = np.full(2 * 5000, 128, np.uint8)
+    o = oracle_for(devices)
+    first = o.run(b, 2)["packages"][0]["offset"]
+    assert first > 4096
+    hushed = b.copy()
+    hushed[: 2 * (first - 40)] = 128  # constant right up to the first pulse: the tile in front of it cannot help
+    streams = [np.concatenate([quiet, a]), np.concatenate([a, quiet, quiet, b]), hushed, np.concatenate([a, hushed])]
+    streams = [s[: len(s) // 16 * 16] for s in streams]
+    gpu = run_gpu(ctx, streams, lib.FMT_CU8, 250000, 433920000)
+    for i, s in enumerate(streams):
+        ref = o.run(s, 2)
+        assert len(ref["packages"]) >= 2
+        check(gpu[i], ref, f"constant cu8 {i}")
+    f = synth.fsk_stream(53)
+    zeros = np.zeros(2 * 7000, np.int16)
+    streams = [np.concatenate([zeros, f]), np.concatenate([f, zeros, f])]
+    streams = [s[: len(s) // 8 * 8] for s in streams]
+    gpu = run_gpu(ctx, streams, lib.FMT_CS16, 1024000, 868000000)
+    for i, s in enumerate(streams):
+        ref = o.run(s, 4, 1024000, 868000000)
+        assert any(p["type"] == 2 for p in ref["packages"])
+        check(gpu[i], ref, f"constant cs16 {i}")
 
 
 def test_against_compiled_reference(ctx, devices):

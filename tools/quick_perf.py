@@ -21,6 +21,7 @@ ap.add_argument("--fsk", action="store_true")
 ap.add_argument("--devices", default="all")
 ap.add_argument("--iters", type=int, default=3)
 ap.add_argument("--pipeline", type=int, default=0)
+ap.add_argument("--bursts", type=int, default=0, help="bursts per OOK stream (0 = synth default)")
 a = ap.parse_args()
 
 n = 1 << a.log2n
@@ -29,7 +30,8 @@ if a.fsk:
     base = [synth.fsk_stream(s, n_samples=n).view(np.uint8) for s in range(a.distinct)]
     fmt, rate, freq = lib.FMT_CS16, 1024000, 868000000
 else:
-    base = [synth.ook_stream(s, n_samples=n) for s in range(a.distinct)]
+    kw = {"n_bursts": a.bursts} if a.bursts else {}
+    base = [synth.ook_stream(s, n_samples=n, **kw) for s in range(a.distinct)]
     fmt, rate, freq = lib.FMT_CU8, 250000, 433920000
 print("generated", a.distinct, "streams in %.1fs" % (time.time() - t))
 per = base[0].nbytes
