@@ -882,10 +882,13 @@ R4_UNROLL(R4_UNROLL_IDLE)
             return cnt;
         };
 
-        // PULSE after the first pulse (no FSK sub-detector): run the high-level and carrier
-        // estimators (src/pulse_detect.c:362-365) speculatively over the chunk, remember their
-        // value in front of every sample, then let every lane test its own sample against the
-        // threshold that value implies.  Everything before the first "below" is exact.
+        // PULSE after the first pulse (no FSK sub-detector): the high-level and carrier estimators
+        // (src/pulse_detect.c:362-365) are 64-sample moving averages with truncation -- inherently
+        // sequential -- but the pulse only ends on a sample below the threshold their value implies.
+        // One step never lifts `high` above max(high, 64 * (am / 64) + 63), so the largest am of the
+        // chunk bounds every threshold of the chunk from above: samples not below THAT threshold
+        // cannot end the pulse.  Advance the two recurrences over exactly those samples; the first
+        // sample that might end the pulse is left to det_step(), which tests it exactly.
         auto pulse_fast = [&](int n) -> int {
             if (d.ook_n == 0) return 0;
             int cnt = nv_tile - n < 32 ? nv_tile - n : 32;
@@ -893,35 +896,32 @@ R4_UNROLL(R4_UNROLL_IDLE)
             int a = (int)(int16_t)(wv & 0xffff);
             int f = (int)(int16_t)(wv >> 16);
             int aq = a / 64, fq = f / 64;
+            int top = lane < cnt ? aq : -512;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                int t = __shfl_xor_sync(0xffffffffu, top, o);
+                top = t > top ? t : top;
+            }
+            int hmax = 64 * top + 63;
+            hmax = d.high > hmax ? d.high : hmax;
+            Thresholds th = det_thresholds(d.low, hmax, p.lv);
+            unsigned m = __ballot_sync(0xffffffffu, lane < cnt && a < th.down);
+            if (m) cnt = __ffs(m) - 1;
+            if (cnt == 0) return 0;
             int h = d.high, g = d.ook_f1; // h >= min_high >= 0 here, so h / 64 == h >> 6
-            int myh = h;
             int const minh = p.lv.min_high;
 R4_UNROLL(R4_UNROLL_PULSE)
             for (int j = 0; j < cnt; ++j) {
-                myh = lane == j ? h : myh;
                 int aj = __shfl_sync(0xffffffffu, aq, j);
                 int fj = __shfl_sync(0xffffffffu, fq, j);
                 h += aj - (int)((unsigned)h >> 6);
                 h = h < minh ? minh : h;
                 g += fj - g / 64;
             }
-            Thresholds th = det_thresholds(d.low, myh, p.lv);
-            unsigned m = __ballot_sync(0xffffffffu, lane < cnt && a < th.down);
-            if (!m) {
-                d.high = h;
-                d.ook_f1 = g;
-                d.run += cnt;
-                return cnt;
-            }
-            int jb = __ffs(m) - 1;
-            d.high = __shfl_sync(0xffffffffu, myh, jb);
-            // the carrier estimate in front of sample jb: redo its (cheap) recurrence up to there
-            g = d.ook_f1;
-#pragma unroll 4
-            for (int j = 0; j < jb; ++j) g += __shfl_sync(0xffffffffu, fq, j) - g / 64;
+            d.high = h;
             d.ook_f1 = g;
-            d.run += jb;
-            return jb; // sample jb ends the pulse: det_step() takes it
+            d.run += cnt;
+            return cnt;
         };
 
         // GAP_START after the first pulse (no FSK feed): thresholds are frozen and nothing happens
