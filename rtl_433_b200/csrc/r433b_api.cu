@@ -68,7 +68,7 @@ struct r433b_ctx {
     cudaStream_t s_in = nullptr, s_det = nullptr, s_out = nullptr;
     static constexpr int kMaxGroups = 16;
     cudaEvent_t ev_in[kMaxGroups]{}, ev_det[kMaxGroups]{}, ev_slc[kMaxGroups]{}, ev_t[4 * kMaxGroups]{}, ev_init = nullptr;
-    DevBuf d_ranges, d_state, d_lengths;
+    DevBuf d_ranges, d_state, d_lengths, d_stage;
     HostBuf h_ranges;
     bool d2h_done = false;
 };
@@ -162,7 +162,7 @@ void r433b_destroy(r433b_ctx *ctx)
     cudaSetDevice(ctx->device);
     for (DevBuf *b : {&ctx->d_data, &ctx->d_offsets, &ctx->d_train, &ctx->d_pkgs, &ctx->d_ppool, &ctx->d_gpool,
                  &ctx->d_counters, &ctx->d_am, &ctx->d_fm, &ctx->d_devparams, &ctx->d_lists, &ctx->d_pairs,
-                 &ctx->d_arena, &ctx->d_cursor, &ctx->d_ranges, &ctx->d_state, &ctx->d_lengths})
+                 &ctx->d_arena, &ctx->d_cursor, &ctx->d_ranges, &ctx->d_state, &ctx->d_lengths, &ctx->d_stage})
         if (b->p) cudaFree(b->p);
     for (HostBuf *b : {&ctx->h_pkgs, &ctx->h_ppool, &ctx->h_gpool, &ctx->h_pairs, &ctx->h_events, &ctx->h_ranges})
         if (b->p) cudaFreeHost(b->p);
@@ -394,7 +394,13 @@ int r433b_process(r433b_ctx *ctx, r433b_batch const *b)
         q.arena = (uint8_t *)ctx->d_arena.p;
         q.arena_cap = ctx->arena_cap;
         q.cursor = (unsigned long long *)ctx->d_cursor.p;
+        q.stage = (uint32_t *)ctx->d_stage.p;
+        q.stage_words = kStageWords;
     };
+    // k_slice always runs as a fixed grid whose CTAs fetch packages (GroupRange::next): every thread
+    // of that grid owns kStageWords of scratch for the staged single pass
+    unsigned const slice_grid = 148 * kSliceCtasPerSm;
+    if (int r = dev_reserve(ctx, ctx->d_stage, (size_t)slice_grid * kSliceThreads * kStageWords * sizeof(uint32_t))) return r;
 
     // ---- pipelined path: host input cut into G TIME SLICES of every stream; the copy-in of slice
     //      k+1 and the copy-out of finished ranges overlap the kernels of slice k (three streams).
@@ -473,7 +479,7 @@ int r433b_process(r433b_ctx *ctx, r433b_batch const *b)
             CU(cudaEventRecord(ctx->ev_t[4 * g + 2], ctx->s_det));
             SliceParams qg = q;
             qg.range = d_rg + g;
-            k_slice<<<148 * 8, kSliceThreads, 0, ctx->s_det>>>(qg);
+            k_slice<<<slice_grid, kSliceThreads, 0, ctx->s_det>>>(qg);
             CU(cudaEventRecord(ctx->ev_t[4 * g + 3], ctx->s_det));
             k_mark<<<1, 1, 0, ctx->s_det>>>(d_rg + g, 3, d_cnt, d_cur);
             CU(cudaMemcpyAsync(h_rg + g, d_rg + g, sizeof(GroupRange), cudaMemcpyDeviceToHost, ctx->s_det));
@@ -583,6 +589,7 @@ int r433b_process(r433b_ctx *ctx, r433b_batch const *b)
     if (ctx->n_pkgs && n_devs) {
         size_t pair_bytes = (size_t)ctx->n_pkgs * n_devs * sizeof(r433b_pair);
         if (int r = dev_reserve(ctx, ctx->d_pairs, pair_bytes)) return r;
+        if (int r = dev_reserve(ctx, ctx->d_ranges, sizeof(GroupRange))) return r;
         for (int attempt = 0; attempt < 3; ++attempt) {
             if (int r = dev_reserve(ctx, ctx->d_arena, ctx->arena_cap)) return r;
             CU(cudaMemsetAsync(ctx->d_pairs.p, 0, pair_bytes, st));
@@ -590,7 +597,11 @@ int r433b_process(r433b_ctx *ctx, r433b_batch const *b)
             SliceParams q{};
             fill_slice(q);
             q.n_pkgs = ctx->n_pkgs;
-            k_slice<<<ctx->n_pkgs, kSliceThreads, 0, st>>>(q);
+            GroupRange all{};
+            all.pkg_end = ctx->n_pkgs;
+            CU(cudaMemcpyAsync(ctx->d_ranges.p, &all, sizeof(all), cudaMemcpyHostToDevice, st));
+            q.range = (GroupRange *)ctx->d_ranges.p;
+            k_slice<<<slice_grid, kSliceThreads, 0, st>>>(q);
             CU(cudaGetLastError());
             slice_launches++;
             CU(cudaMemcpyAsync(cursor, ctx->d_cursor.p, sizeof(cursor), cudaMemcpyDeviceToHost, st));

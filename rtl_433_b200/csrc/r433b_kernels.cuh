@@ -1023,7 +1023,7 @@ struct GroupRange {
     unsigned long long arena_begin, arena_end;
     unsigned long long events_end;
     unsigned overflow;
-    unsigned next; // k_slice work counter: next package of this range to hand to a CTA
+    unsigned next; // k_slice work counter: next (package, device group) item of this range, relative to pkg_begin
 };
 
 __global__ void k_mark(GroupRange *r, int which, unsigned const *counters, unsigned long long const *cursor)
@@ -1035,7 +1035,7 @@ __global__ void k_mark(GroupRange *r, int which, unsigned const *counters, unsig
         r->pkg_end = counters[0];
         r->pool_end = counters[1];
         r->overflow = counters[2];
-        r->next = r->pkg_begin;
+        r->next = 0;
     } else if (which == 2) {
         r->arena_begin = cursor[0];
     } else {
@@ -1048,7 +1048,7 @@ __global__ void k_mark(GroupRange *r, int which, unsigned const *counters, unsig
 struct SliceParams {
     r433b_package *pkgs;
     unsigned n_pkgs;
-    GroupRange *range; // if set: packages [pkg_begin, min(pkg_end, n_pkgs)) instead of [0, n_pkgs)
+    GroupRange *range; // packages [pkg_begin, min(pkg_end, n_pkgs)) and the work counter
     int const *pulse_pool, *gap_pool;
     SlicerParams const *dev;  // per device, already scaled to the batch sample rate
     unsigned n_devs;
@@ -1058,50 +1058,57 @@ struct SliceParams {
     uint8_t *arena;
     unsigned long long arena_cap;
     unsigned long long *cursor; // [0] bytes reserved, [1] events, [2] overflow
+    uint32_t *stage;            // stage_words per thread of the (fixed, ranged) grid, or nullptr
+    unsigned stage_words;
 };
 
 constexpr int kSliceThreads = 128;
+constexpr unsigned kStageWords = 1024; // scratch words per k_slice thread (4 KiB): larger outputs take the second pass
 constexpr int kSliceCtasPerSm = 16; // 32 registers, 64 warps/SM: latency hiding beats the spills (measured 34.8 -> 27.8 ms)
 
 __global__ void __launch_bounds__(kSliceThreads, kSliceCtasPerSm) k_slice(SliceParams p)
 {
-    // Without a range: one CTA per package (the grid is the package count).  With a range (pipelined
-    // path, package count unknown to the host): a fixed grid whose CTAs fetch packages one at a time.
-    __shared__ unsigned s_pk;
-    unsigned pk_end = p.n_pkgs;
-    if (p.range) pk_end = p.range->pkg_end < p.n_pkgs ? p.range->pkg_end : p.n_pkgs;
+    // A fixed grid of independent WARPS.  A work item is (package, group of 32 devices of the list
+    // that takes the package type); every warp fetches items from the range's counter until the
+    // range is exhausted.  (One CTA per package left most warps waiting at the CTA barrier for the
+    // slowest device group: 48 % of all stall samples.)
+    unsigned const lane = threadIdx.x & 31;
+    unsigned const groups = ((p.n_ook > p.n_fsk ? p.n_ook : p.n_fsk) + 31) / 32;
+    if (!groups) return;
+    unsigned const pk_begin = p.range->pkg_begin;
+    unsigned const pk_end = p.range->pkg_end < p.n_pkgs ? p.range->pkg_end : p.n_pkgs;
+    // Staging: the first run of the slicer writes its words into a per-thread scratch region; if
+    // every lane's output fitted, the warp reserves arena space and copies the regions over
+    // (coalesced, lane by lane) instead of running the slicers a second time.
+    uint32_t *stage = p.stage ? p.stage + ((size_t)blockIdx.x * kSliceThreads + threadIdx.x) * p.stage_words : nullptr;
+    unsigned const stage_words = stage ? p.stage_words : 0;
     for (;;) {
-    unsigned pk;
-    if (p.range) {
-        __syncthreads();
-        if (threadIdx.x == 0) s_pk = atomicAdd(&p.range->next, 1u);
-        __syncthreads();
-        pk = s_pk;
-    } else {
-        pk = blockIdx.x;
-    }
-    if (pk >= pk_end) break;
-    r433b_package const k = p.pkgs[pk];
-    unsigned const n_list = k.type == 1 ? p.n_ook : p.n_fsk;
-    unsigned const *list = k.type == 1 ? p.ook_list : p.fsk_list;
-    if (threadIdx.x == 0) p.pkgs[pk].first_pair = pk * p.n_devs;
+        unsigned item = 0;
+        if (lane == 0) item = atomicAdd(&p.range->next, 1u);
+        item = __shfl_sync(0xffffffffu, item, 0);
+        unsigned const rel = item / groups, g = item - rel * groups;
+        if (rel >= pk_end - pk_begin || pk_end <= pk_begin) break;
+        unsigned const pk = pk_begin + rel;
+        r433b_package const k = p.pkgs[pk];
+        unsigned const n_list = k.type == 1 ? p.n_ook : p.n_fsk;
+        unsigned const *list = k.type == 1 ? p.ook_list : p.fsk_list;
+        if (g == 0 && lane == 0) p.pkgs[pk].first_pair = pk * p.n_devs;
+        if (g * 32 >= n_list) continue;
 
-    PulseView pv;
-    pv.pulse = p.pulse_pool + k.pulse_off;
-    pv.gap = p.gap_pool + k.pulse_off;
-    pv.n = k.num_pulses;
+        PulseView pv;
+        pv.pulse = p.pulse_pool + k.pulse_off;
+        pv.gap = p.gap_pool + k.pulse_off;
+        pv.n = k.num_pulses;
 
-    for (unsigned base = 0; base < n_list; base += blockDim.x) {
-        unsigned slot = base + threadIdx.x;
-        bool active = slot < n_list;
-        unsigned dev = active ? list[slot] : 0;
-        unsigned lane = threadIdx.x & 31;
+        unsigned const slot = g * 32 + lane;
+        bool const active = slot < n_list;
+        unsigned const dev = active ? list[slot] : 0;
         unsigned bytes = 0, nev = 0;
         unsigned long long off = 0;
         bool fits = false;
         SlicerParams sp;
         if (active) sp = p.dev[dev];
-        // pass 0 counts, pass 1 stores; one copy of the slicer code serves both
+        // pass 0 counts (and stages), pass 1 stores; one copy of the slicer code serves both
 #pragma unroll 1
         for (int pass = 0; pass < 2; ++pass) {
             if (pass == 1) {
@@ -1125,10 +1132,29 @@ __global__ void __launch_bounds__(kSliceThreads, kSliceCtasPerSm) k_slice(SliceP
                 off = wbase + incl - bytes;
                 fits = off + bytes <= p.arena_cap;
                 if (active && bytes && !fits) atomicOr(p.cursor + 2, 1ull);
+                bool const staged = bytes <= stage_words * 4;
+                if (__all_sync(0xffffffffu, !active || !bytes || staged)) {
+                    __syncwarp();
+                    unsigned todo = __ballot_sync(0xffffffffu, active && bytes && fits);
+                    while (todo) {
+                        int const l = __ffs(todo) - 1;
+                        todo &= todo - 1;
+                        unsigned const wl = __shfl_sync(0xffffffffu, bytes, l) / 4;
+                        unsigned long long const ol = __shfl_sync(0xffffffffu, off, l);
+                        uint32_t const *from = stage + ((long long)l - (long long)lane) * (long long)stage_words;
+                        uint32_t *to = reinterpret_cast<uint32_t *>(p.arena + ol);
+                        for (unsigned i = lane; i < wl; i += 32) __stcs(to + i, from[i]);
+                    }
+                    __syncwarp();
+                    break;
+                }
             }
             if (active && (pass == 0 || (bytes && fits))) {
                 EventWriter w;
-                w.init(pass ? reinterpret_cast<uint32_t *>(p.arena + off) : nullptr, bytes / 4);
+                if (pass)
+                    w.init(reinterpret_cast<uint32_t *>(p.arena + off), bytes / 4);
+                else
+                    w.init(stage, stage_words);
                 slice_dispatch(pv, sp, w);
                 if (pass == 0) {
                     bytes = w.committed * 4;
@@ -1144,8 +1170,6 @@ __global__ void __launch_bounds__(kSliceThreads, kSliceCtasPerSm) k_slice(SliceP
             p.pairs[(size_t)pk * p.n_devs + dev] = pr;
         }
     }
-    if (!p.range) break;
-    } // packages of this CTA
 }
 
 } // namespace r433b
