@@ -842,19 +842,28 @@ R4_UNROLL(R4_UNROLL_IDLE)
         };
 
         // GAP: thresholds are frozen; the next event is the first sample above `up` or the run
-        // length reaching an end-of-package limit (src/pulse_detect.c:422-470).
+        // length reaching an end-of-package limit (src/pulse_detect.c:422-470).  Look for either in
+        // the rest of the tile, 32 samples per ballot.
         auto gap_fast = [&](int n) -> int {
             if (d.eop_flag) return 0;
-            int cnt = nv_tile - n < 32 ? nv_tile - n : 32;
+            int const cnt = nv_tile - n;
             Thresholds th = det_thresholds(d.low, d.high, p.lv);
-            int a = lane < cnt ? (int)(int16_t)(tile[word_index<C, W>(n + lane)] & 0xffff) : -32768;
-            unsigned m = __ballot_sync(0xffffffffu, lane < cnt && a > th.up);
-            int ja = m ? __ffs(m) - 1 : 32;
             long long lim_a = 10ll * d.longest > 10ll * per_ms ? 10ll * d.longest : 10ll * per_ms;
             long long lim_b = 100ll * per_ms;
             long long rstar = (lim_a < lim_b ? lim_a : lim_b) + 1; // first run length that ends the package
             long long je = rstar - d.run - 1;
             if (je < 0) je = 0;
+            int const horizon = je < cnt ? (int)je + 1 : cnt; // samples that matter
+            int ja = 0x7fffffff;
+#pragma unroll 1
+            for (int base = 0; base < horizon; base += 32) {
+                int a = base + lane < cnt ? (int)(int16_t)(tile[word_index<C, W>(n + base + lane)] & 0xffff) : -32768;
+                unsigned m = __ballot_sync(0xffffffffu, a > th.up);
+                if (m) {
+                    ja = base + __ffs(m) - 1;
+                    break;
+                }
+            }
             if (ja < cnt && ja <= je) { // a new pulse starts first
                 d.run += ja + 1;
                 put(tr.ook_gap, d.ook_hw, d.ook_n, d.run);
