@@ -366,6 +366,19 @@ int r433b_process(r433b_ctx *ctx, r433b_batch const *b)
     };
     std::sort(ook.begin(), ook.end(), by_mod);
     std::sort(fsk.begin(), fsk.end(), by_mod);
+    // one k_slice work item is 32 consecutive list slots: start every modulation on a multiple of
+    // 32 (holes = kNoDevice) so that a warp never runs two slicers one after the other
+    auto align_groups = [&](std::vector<unsigned> &v) {
+        std::vector<unsigned> out;
+        for (size_t i = 0; i < v.size(); ++i) {
+            if (i && ctx->devs[v[i]].modulation != ctx->devs[v[i - 1]].modulation)
+                while (out.size() % 32) out.push_back(kNoDevice);
+            out.push_back(v[i]);
+        }
+        v.swap(out);
+    };
+    align_groups(ook);
+    align_groups(fsk);
     ctx->n_ook = (unsigned)ook.size();
     ctx->n_fsk = (unsigned)fsk.size();
     if (int r = dev_reserve(ctx, ctx->d_devparams, std::max<size_t>(1, n_devs) * sizeof(SlicerParams))) return r;

@@ -1072,6 +1072,7 @@ struct SliceParams {
 };
 
 constexpr int kSliceThreads = 128;
+constexpr unsigned kNoDevice = 0xffffffffu; // hole in a device list (alignment padding)
 constexpr unsigned kStageWords = 1024; // scratch words per k_slice thread (4 KiB): larger outputs take the second pass
 constexpr int kSliceCtasPerSm = 16; // 32 registers, 64 warps/SM: latency hiding beats the spills (measured 34.8 -> 27.8 ms)
 
@@ -1095,8 +1096,11 @@ __global__ void __launch_bounds__(kSliceThreads, kSliceCtasPerSm) k_slice(SliceP
         unsigned item = 0;
         if (lane == 0) item = atomicAdd(&p.range->next, 1u);
         item = __shfl_sync(0xffffffffu, item, 0);
-        unsigned const rel = item / groups, g = item - rel * groups;
-        if (rel >= pk_end - pk_begin || pk_end <= pk_begin) break;
+        // device group major: at any moment most warps of the GPU run the same slicer (instruction cache)
+        if (pk_end <= pk_begin) break;
+        unsigned const n_rel = pk_end - pk_begin;
+        unsigned const g = item / n_rel, rel = item - g * n_rel;
+        if (g >= groups) break;
         unsigned const pk = pk_begin + rel;
         r433b_package const k = p.pkgs[pk];
         unsigned const n_list = k.type == 1 ? p.n_ook : p.n_fsk;
@@ -1110,8 +1114,8 @@ __global__ void __launch_bounds__(kSliceThreads, kSliceCtasPerSm) k_slice(SliceP
         pv.n = k.num_pulses;
 
         unsigned const slot = g * 32 + lane;
-        bool const active = slot < n_list;
-        unsigned const dev = active ? list[slot] : 0;
+        unsigned const dev = slot < n_list ? list[slot] : kNoDevice;
+        bool const active = dev != kNoDevice;
         unsigned bytes = 0, nev = 0;
         unsigned long long off = 0;
         bool fits = false;
