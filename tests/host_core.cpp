@@ -349,4 +349,79 @@ int32_t const *hc_gap_pool(void *p) { return ((Hc *)p)->gpool.data(); }
 int16_t const *hc_am(void *p) { return ((Hc *)p)->am.data(); }
 int16_t const *hc_fm(void *p) { return ((Hc *)p)->fm.data(); }
 
+
+// ---- invariants the warp-level kernel code relies on, checked on the product's own functions ----
+
+// k_detect's PULSE fast path: one step of the high-level estimator never lifts it above
+// max(high, 64 * (am / 64) + 63), and the "below" threshold never falls when high grows -- so the
+// largest sample of a chunk bounds every threshold of the chunk.  Returns the number of violations.
+int hc_check_pulse_bound(unsigned seed, int trials)
+{
+    srand(seed);
+    int bad = 0;
+    for (int t = 0; t < trials; ++t) {
+        Levels lv = compute_levels(0, (t % 5 == 0) ? -10.0f : 0.0f, -12.1442f - (float)(t % 7), 9.0f);
+        int const minh = lv.min_high;
+        int h = minh + rand() % 30000;
+        int low = rand() % 4000;
+        int base = rand() % 32000, spread = 1 + rand() % (t % 3 ? 400 : 20000);
+        int a[32], top = -512;
+        for (int j = 0; j < 32; ++j) {
+            int v = base + rand() % spread - spread / 2;
+            a[j] = v < 0 ? 0 : (v > 32767 ? 32767 : v);
+            if (a[j] / 64 > top) top = a[j] / 64;
+        }
+        int hmax = 64 * top + 63;
+        if (h > hmax) hmax = h;
+        Thresholds tmax = det_thresholds(low, hmax, lv);
+        for (int j = 0; j < 32; ++j) {
+            if (h > hmax) bad++;
+            if (det_thresholds(low, h, lv).down > tmax.down) bad++;
+            h += a[j] / 64 - (int)((unsigned)h >> 6);
+            if (h < minh) h = minh;
+        }
+        if (h > hmax) bad++;
+    }
+    return bad;
+}
+
+// k_detect's FM on demand: the (provably non-wrapping) low-pass is monotone in its state, so when the
+// two ends of the full range have met after some samples, EVERY start state has met them too.
+// Runs `trials` random discriminator sequences of `len` samples through the cu8 (cs16 = 0) or cs16
+// filter at `rate`; returns -1 on a violation, else how many sequences collapsed.
+int hc_check_bracket_rebuild(unsigned seed, int trials, int cs16, unsigned rate, int len, int noise)
+{
+    srand(seed);
+    int a1 = 0, b0 = 0;
+    fm_coeffs(cs16, rate, 0.1f, a1, b0);
+    long long unity = cs16 ? (1ll << 30) : 16384ll;
+    if (!(a1 >= 0 && b0 >= 0 && (long long)a1 + 2ll * b0 <= unity)) return -2;
+    int collapsed = 0;
+    std::vector<long long> x((size_t)len + 1);
+    for (int t = 0; t < trials; ++t) {
+        long long lim = cs16 ? 0x7fffffffll : 32767ll;
+        long long centre = (long long)(rand() % 2001 - 1000) * (lim / 1000);
+        for (int j = 0; j <= len; ++j) {
+            long long v = noise ? centre + (long long)(rand() % (2 * noise + 1) - noise) * (cs16 ? 65536 : 1) : centre;
+            x[(size_t)j] = v < -lim - 1 ? -lim - 1 : (v > lim ? lim : v);
+        }
+        auto run = [&](int y) {
+            for (int j = 1; j <= len; ++j) {
+                long long s = x[(size_t)j] + x[(size_t)j - 1];
+                y = cs16 ? iir32(y, a1, b0, s) : iir16_nowrap(y, a1, b0, (int)s);
+            }
+            return y;
+        };
+        int lo = run(cs16 ? (int)0x80000000 : -32768), hi = run(cs16 ? 0x7fffffff : 32767);
+        if (lo > hi) return -1;
+        for (int k = 0; k < 8; ++k) {
+            int y0 = cs16 ? (int)((unsigned)rand() * 2654435761u) : rand() % 65536 - 32768;
+            int y = run(y0);
+            if (y < lo || y > hi) return -1;
+        }
+        if (lo == hi) collapsed++;
+    }
+    return collapsed;
+}
+
 } // extern "C"
