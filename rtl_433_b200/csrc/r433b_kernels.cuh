@@ -933,6 +933,44 @@ R4_UNROLL(R4_UNROLL_PULSE)
             return cnt;
         };
 
+        // PULSE of the FIRST pulse: the same bound, with the FSK sub-detector fed in the loop
+        // (src/pulse_detect.c:367-371).  An FSK transmission is one long OOK "pulse", so this is the
+        // hot loop of FSK captures; det_step() would re-derive thresholds and re-dispatch per sample.
+        auto pulse0_fast = [&](int n) -> int {
+            int cnt = nv_tile - n < 32 ? nv_tile - n : 32;
+            uint32_t wv = lane < cnt ? tile[word_index<C, W>(n + lane)] : 0x00007fffu;
+            int a = (int)(int16_t)(wv & 0xffff);
+            int f = (int)(int16_t)(wv >> 16);
+            int aq = a / 64;
+            int top = lane < cnt ? aq : -512;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                int t = __shfl_xor_sync(0xffffffffu, top, o);
+                top = t > top ? t : top;
+            }
+            int hmax = 64 * top + 63;
+            hmax = d.high > hmax ? d.high : hmax;
+            Thresholds th = det_thresholds(d.low, hmax, p.lv);
+            unsigned m = __ballot_sync(0xffffffffu, lane < cnt && a < th.down);
+            if (m) cnt = __ffs(m) - 1;
+            if (cnt == 0) return 0;
+            int const minh = p.lv.min_high;
+#pragma unroll 1
+            for (int j = 0; j < cnt; ++j) {
+                int aj = __shfl_sync(0xffffffffu, aq, j);
+                int fj = __shfl_sync(0xffffffffu, f, j);
+                d.high += aj - (int)((unsigned)d.high >> 6);
+                d.high = d.high < minh ? minh : d.high;
+                d.ook_f1 += fj / 64 - d.ook_f1 / 64;
+                if (p.fpdm == 0)
+                    fsk_classic(d, tr, fj, cx);
+                else
+                    fsk_minmax(d, tr, fj, cx);
+            }
+            d.run += cnt;
+            return cnt;
+        };
+
         // GAP_START after the first pulse (no FSK feed): thresholds are frozen and nothing happens
         // until either a sample rises above `up` (spurious gap) or the run reaches 10 samples.
         // Skip the uneventful samples in front of that transition; det_step() takes the transition.
@@ -966,7 +1004,7 @@ R4_UNROLL(R4_UNROLL_PULSE)
             else if (d.st == kGap)
                 adv = gap_fast(n);
             else if (d.st == kPulse)
-                adv = pulse_fast(n);
+                adv = d.ook_n ? pulse_fast(n) : pulse0_fast(n);
             else
                 adv = gapstart_fast(n);
             if (adv) {
