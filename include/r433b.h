@@ -36,6 +36,9 @@ extern "C" {
 #define R433B_FMT_CU8 2  /* bytes per IQ sample; dm_state.sample_size, include/r_private.h:39 */
 #define R433B_FMT_CS16 4
 #define R433B_FMT_CS8 0x102 /* signed 8-bit IQ: converted to cu8 (+128) while loading, src/rtl_433.c:1830-1834 */
+#define R433B_FMT_CF32 0x204 /* float IQ (8 bytes per sample in `data`; offsets multiples of 32): clamped and
+                               scaled to cs16 on the device first, src/rtl_433.c:1811-1825; results, block size
+                               and file positions are those of the cs16 stream, as in the reference */
 
 #define R433B_FPDM_CLASSIC 0 /* FSK_PULSE_DETECT_OLD,  include/pulse_detect.h:29-34 */
 #define R433B_FPDM_MINMAX 1  /* FSK_PULSE_DETECT_NEW  */

@@ -42,6 +42,7 @@ def lib():
         L.orc_set_fm_low_pass.argtypes = [C.c_void_p, C.c_float]
         L.orc_add_device.argtypes = [C.c_void_p, C.POINTER(Device)]
         L.orc_num_devices.argtypes = [C.c_void_p]
+        L.orc_cf32_to_cs16.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
         L.orc_run_stream.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_uint32, C.c_uint32, C.c_int,
                                      C.c_uint32]
         for name, res in [("orc_packages", C.POINTER(Package)), ("orc_events", C.POINTER(Event)),
@@ -93,6 +94,13 @@ class Oracle:
 
     def set_fm_low_pass(self, v):
         self.L.orc_set_fm_low_pass(self.h, v)
+
+    def cf32_to_cs16(self, floats):
+        """src/rtl_433.c:1811-1825 on a float32 array -> int16 array of the same length."""
+        x = np.ascontiguousarray(floats, np.float32)
+        out = np.empty(len(x), np.int16)
+        self.L.orc_cf32_to_cs16(x.ctypes.data, out.ctypes.data, len(x))
+        return out
 
     def run_raw(self, iq, sample_size, samp_rate=250000, center_freq=433920000, fpdm=2, block_bytes=0):
         iq = np.ascontiguousarray(iq)

@@ -1192,6 +1192,23 @@ orc_t *orc_create(void)
     return o;
 }
 
+// src/rtl_433.c:1811-1825: a cf32 capture is turned into cs16 while it is read, block by block:
+// "clamp float to [-1,1] and scale to Q0.15".  The float -> int conversion of an out-of-range
+// or NaN product is undefined in C; on the reference's x86-64 builds (cvttss2si) it yields
+// INT_MIN, which the clamp turns into -INT16_MAX.  Restated with that behaviour made explicit.
+void orc_cf32_to_cs16(float const *in, int16_t *out, size_t n)
+{
+    for (size_t i = 0; i < n; ++i) {
+        float v = in[i] * INT16_MAX;
+        int s_tmp = (v >= -2147483648.0f && v < 2147483648.0f) ? (int)v : INT32_MIN;
+        if (s_tmp < -INT16_MAX)
+            s_tmp = -INT16_MAX;
+        else if (s_tmp > INT16_MAX)
+            s_tmp = INT16_MAX;
+        out[i] = (int16_t)s_tmp;
+    }
+}
+
 void orc_destroy(orc_t *o)
 {
     if (!o) return;

@@ -65,6 +65,9 @@ int orc_add_device(orc_t *o, orc_device const *d);
 int orc_num_devices(orc_t *o);
 
 /* one capture file: block loop + flush + reset, as rtl_433 -r does */
+/* src/rtl_433.c:1811-1825 */
+void orc_cf32_to_cs16(float const *in, int16_t *out, size_t n);
+
 int orc_run_stream(orc_t *o, void const *iq, size_t bytes, int sample_size, uint32_t samp_rate,
         uint32_t center_freq, int fpdm_mode, uint32_t block_bytes);
 

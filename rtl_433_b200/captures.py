@@ -100,7 +100,7 @@ def parse_capture_name(spec):
     return info
 
 
-_ABI_FORMAT = {"cu8": lib.FMT_CU8, "cs8": lib.FMT_CS8, "cs16": lib.FMT_CS16}
+_ABI_FORMAT = {"cu8": lib.FMT_CU8, "cs8": lib.FMT_CS8, "cs16": lib.FMT_CS16, "cf32": lib.FMT_CF32}
 
 
 def load_batches(specs, default_rate=DEFAULT_RATE, default_freq=DEFAULT_FREQ):
@@ -110,17 +110,18 @@ def load_batches(specs, default_rate=DEFAULT_RATE, default_freq=DEFAULT_FREQ):
     for spec in specs:
         info = parse_capture_name(spec)
         if info["format"] not in _ABI_FORMAT:
-            raise ValueError(f"{spec}: format {info['format']!r} is not on the GPU path (cu8, cs8, cs16 are)")
+            raise ValueError(f"{spec}: format {info['format']!r} is not on the GPU path (cu8, cs8, cs16, cf32 are)")
         key = (info["format"], info["sample_rate"] or default_rate, info["center_frequency"] or default_freq)
         groups.setdefault(key, []).append(info["path"])
     out = []
     for (fmt, rate, freq), paths in groups.items():
-        ss = 2 if fmt in ("cu8", "cs8") else 4
+        ss = {"cu8": 2, "cs8": 2, "cs16": 4, "cf32": 8}[fmt]
+        align = 32 if fmt == "cf32" else 16
         bufs = [np.fromfile(p, dtype=np.uint8) for p in paths]
         lengths = np.array([len(b) // ss * ss for b in bufs], np.uint64)  # a trailing partial sample is dropped
         offsets = np.zeros(len(bufs) + 1, np.uint64)
         for i, n in enumerate(lengths):
-            offsets[i + 1] = offsets[i] + (int(n) + 15) // 16 * 16
+            offsets[i + 1] = offsets[i] + (int(n) + align - 1) // align * align
         data = np.zeros(int(offsets[-1]), np.uint8)
         for i, b in enumerate(bufs):
             data[int(offsets[i]):int(offsets[i]) + int(lengths[i])] = b[:int(lengths[i])]
@@ -156,7 +157,7 @@ def replay(specs, protocols=None, cuda_device=0, max_rows=8, out=print):
             for i, path in enumerate(batch["files"]):
                 pk = res["packages"][res["packages"]["stream"] == i]
                 out(f"{path}: {batch['format']} {batch['sample_rate']} S/s {batch['center_frequency']} Hz, "
-                    f"{int(batch['lengths'][i]) // (2 if batch['abi_format'] != lib.FMT_CS16 else 4)} samples, {len(pk)} package(s)")
+                    f"{int(batch['lengths'][i]) // {lib.FMT_CU8: 2, lib.FMT_CS8: 2, lib.FMT_CS16: 4, lib.FMT_CF32: 8}[batch['abi_format']]} samples, {len(pk)} package(s)")
                 events = []
 
                 def on_event(pkg, dev, pd, bb, events=events):

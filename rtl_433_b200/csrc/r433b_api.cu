@@ -68,7 +68,7 @@ struct r433b_ctx {
     cudaStream_t s_in = nullptr, s_det = nullptr, s_out = nullptr;
     static constexpr int kMaxGroups = 16;
     cudaEvent_t ev_in[kMaxGroups]{}, ev_det[kMaxGroups]{}, ev_slc[kMaxGroups]{}, ev_t[4 * kMaxGroups]{}, ev_init = nullptr;
-    DevBuf d_ranges, d_state, d_lengths, d_stage;
+    DevBuf d_ranges, d_state, d_lengths, d_stage, d_raw;
     HostBuf h_ranges;
     bool d2h_done = false;
 };
@@ -162,7 +162,7 @@ void r433b_destroy(r433b_ctx *ctx)
     cudaSetDevice(ctx->device);
     for (DevBuf *b : {&ctx->d_data, &ctx->d_offsets, &ctx->d_train, &ctx->d_pkgs, &ctx->d_ppool, &ctx->d_gpool,
                  &ctx->d_counters, &ctx->d_am, &ctx->d_fm, &ctx->d_devparams, &ctx->d_lists, &ctx->d_pairs,
-                 &ctx->d_arena, &ctx->d_cursor, &ctx->d_ranges, &ctx->d_state, &ctx->d_lengths, &ctx->d_stage})
+                 &ctx->d_arena, &ctx->d_cursor, &ctx->d_ranges, &ctx->d_state, &ctx->d_lengths, &ctx->d_stage, &ctx->d_raw})
         if (b->p) cudaFree(b->p);
     for (HostBuf *b : {&ctx->h_pkgs, &ctx->h_ppool, &ctx->h_gpool, &ctx->h_pairs, &ctx->h_events, &ctx->h_ranges})
         if (b->p) cudaFreeHost(b->p);
@@ -235,15 +235,20 @@ int r433b_set_r_devices(r433b_ctx *ctx, struct r_device *const *devs, uint32_t n
 int r433b_process(r433b_ctx *ctx, r433b_batch const *b)
 {
     if (!ctx || !b || !b->offsets || (b->n_streams && !b->data)) return fail(ctx, R433B_EINVAL, "null argument");
-    if (b->sample_format != R433B_FMT_CU8 && b->sample_format != R433B_FMT_CS16 && b->sample_format != R433B_FMT_CS8)
-        return fail(ctx, R433B_EINVAL, "sample_format must be R433B_FMT_CU8, _CS8 or _CS16");
+    if (b->sample_format != R433B_FMT_CU8 && b->sample_format != R433B_FMT_CS16 && b->sample_format != R433B_FMT_CS8
+            && b->sample_format != R433B_FMT_CF32)
+        return fail(ctx, R433B_EINVAL, "sample_format must be R433B_FMT_CU8, _CS8, _CS16 or _CF32");
+    // cf32 becomes cs16 on the device before anything else (src/rtl_433.c:1811-1825): from here on
+    // offsets, lengths and byte counts are those of the cs16 stream (half the cf32 ones)
+    bool const cf32 = b->sample_format == R433B_FMT_CF32;
+    unsigned const in_div = cf32 ? 2 : 1;
     if (b->samp_rate == 0) return fail(ctx, R433B_EINVAL, "samp_rate is 0");
     int const SS = (int)(b->sample_format & 0xff); // bytes per IQ sample; cs8 is cu8 after the load-time +128
     uint32_t block_bytes = b->block_bytes ? b->block_bytes : 262144u;
     int const T = SS == 2 ? TileCfg<2>::T : TileCfg<4>::T;
     if (block_bytes % (uint32_t)(T * SS) != 0) return fail(ctx, R433B_EINVAL, "block_bytes must be a multiple of 2048");
     for (uint32_t i = 0; i <= b->n_streams; ++i) {
-        if (b->offsets[i] % 16) return fail(ctx, R433B_EINVAL, "stream offsets must be multiples of 16 bytes");
+        if (b->offsets[i] % (16 * in_div)) return fail(ctx, R433B_EINVAL, "stream offsets must be multiples of 16 bytes (32 for cf32)");
         if (i && b->offsets[i] < b->offsets[i - 1]) return fail(ctx, R433B_EINVAL, "offsets not ascending");
     }
     CU(cudaSetDevice(ctx->device));
@@ -252,15 +257,17 @@ int r433b_process(r433b_ctx *ctx, r433b_batch const *b)
     ctx->batch.sample_format = (uint32_t)SS; // the host replay only needs the sample size (dm_state.sample_size)
     ctx->batch.block_bytes = block_bytes;
     ctx->offsets.assign(b->offsets, b->offsets + b->n_streams + 1);
+    for (auto &v : ctx->offsets) v /= in_div;
     ctx->batch.offsets = ctx->offsets.data();
     ctx->lengths.resize(b->n_streams);
     for (uint32_t i = 0; i < b->n_streams; ++i) {
         uint64_t gap = b->offsets[i + 1] - b->offsets[i];
         ctx->lengths[i] = b->lengths ? b->lengths[i] : gap;
         if (ctx->lengths[i] > gap) return fail(ctx, R433B_EINVAL, "lengths[i] exceeds the gap to the next offset");
+        if (cf32) ctx->lengths[i] = ctx->lengths[i] / 8 * 4; // whole IQ pairs of floats -> cs16 bytes
     }
     ctx->batch.lengths = ctx->lengths.data();
-    uint64_t const total_bytes = b->n_streams ? b->offsets[b->n_streams] : 0;
+    uint64_t const total_bytes = b->n_streams ? b->offsets[b->n_streams] / in_div : 0;
     uint64_t used_bytes = 0;
     for (uint64_t v : ctx->lengths) used_bytes += v;
     uint32_t const n_devs = (uint32_t)ctx->devs.size();
@@ -276,12 +283,14 @@ int r433b_process(r433b_ctx *ctx, r433b_batch const *b)
 
     // ---- device buffers and launch parameters (no data moved yet) -----------------------
     uint8_t const *d_in;
-    if (b->data_on_device) {
+    if (b->data_on_device && !cf32) {
         d_in = (uint8_t const *)b->data;
     } else {
         if (int r = dev_reserve(ctx, ctx->d_data, total_bytes + 64)) return r;
         d_in = (uint8_t const *)ctx->d_data.p;
     }
+    if (cf32 && !b->data_on_device)
+        if (int r = dev_reserve(ctx, ctx->d_raw, 2 * total_bytes + 64)) return r;
     if (int r = dev_reserve(ctx, ctx->d_offsets, (b->n_streams + 1) * sizeof(uint64_t))) return r;
     CU(cudaMemcpy(ctx->d_offsets.p, ctx->offsets.data(), (b->n_streams + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice));
     if (int r = dev_reserve(ctx, ctx->d_lengths, std::max<size_t>(1, b->n_streams) * sizeof(uint64_t))) return r;
@@ -429,7 +438,7 @@ int r433b_process(r433b_ctx *ctx, r433b_batch const *b)
     if (G == 0) // measured on B200 (tools/e2e_sweep.py): many slices of >= 128 KiB per stream beat fewer, larger ones
         G = (total_bytes >= (256ull << 20) && stride >= (1u << 20)) ? (int)std::min<uint64_t>(r433b_ctx::kMaxGroups, stride / (128u << 10)) : 1;
     if (b->data_on_device && ctx->pipeline_groups == 0) G = 1; // device input: slices only when asked for
-    if (b->want_stages || !n_devs || !uniform) G = 1;
+    if (b->want_stages || !n_devs || !uniform || cf32) G = 1;
     uint64_t slice_samples = 0;
     if (G > 1) {
         uint64_t n_samp = stride / SS;
@@ -564,7 +573,16 @@ int r433b_process(r433b_ctx *ctx, r433b_batch const *b)
 
     // ---- sequential path ------------------------------------------------------------------
     CU(cudaEventRecord(ctx->ev[0], st));
-    if (!b->data_on_device && total_bytes)
+    if (cf32 && total_bytes) {
+        void const *raw = b->data;
+        if (!b->data_on_device) {
+            CU(cudaMemcpyAsync(ctx->d_raw.p, b->data, 2 * total_bytes, cudaMemcpyHostToDevice, st));
+            raw = ctx->d_raw.p;
+        }
+        size_t n4 = (size_t)(2 * total_bytes / 16); // groups of four floats (offsets are multiples of 32 bytes)
+        k_cf32_to_cs16<<<148 * 8, 256, 0, st>>>((float4 const *)raw, (uint2 *)ctx->d_data.p, n4);
+        CU(cudaGetLastError());
+    } else if (!b->data_on_device && total_bytes)
         CU(cudaMemcpyAsync(ctx->d_data.p, b->data, total_bytes, cudaMemcpyHostToDevice, st));
     CU(cudaEventRecord(ctx->ev[1], st));
 

@@ -1060,6 +1060,32 @@ R4_UNROLL(R4_UNROLL_PULSE)
     }
 }
 
+// ----------------------------------------------------------------- cf32 -> cs16 ----------
+
+// src/rtl_433.c:1811-1825: "clamp float to [-1,1] and scale to Q0.15" -- the reference converts a
+// cf32 capture to cs16 before anything else looks at it.  Streaming, HBM bound (12 B per float pair
+// of traffic per 2 samples); `n4` groups of four floats.  The out-of-range / NaN case follows the
+// reference's x86-64 builds: the conversion yields INT_MIN, the clamp makes it -32767.
+__global__ void k_cf32_to_cs16(float4 const *in, uint2 *out, size_t n4)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+        float4 v = __ldcs(in + i);
+        float f[4] = {v.x, v.y, v.z, v.w};
+        int s[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            float t = __fmul_rn(f[k], 32767.0f);
+            int q = (t >= -2147483648.0f && t < 2147483648.0f) ? __float2int_rz(t) : (int)0x80000000;
+            q = q < -32767 ? -32767 : (q > 32767 ? 32767 : q);
+            s[k] = q;
+        }
+        uint2 o;
+        o.x = (uint32_t)(uint16_t)(int16_t)s[0] | ((uint32_t)(uint16_t)(int16_t)s[1] << 16);
+        o.y = (uint32_t)(uint16_t)(int16_t)s[2] | ((uint32_t)(uint16_t)(int16_t)s[3] << 16);
+        out[i] = o;
+    }
+}
+
 // ------------------------------------------------------------------------- k_slice -------
 
 // What one pipeline group (a contiguous run of streams) produced, filled on the device so the

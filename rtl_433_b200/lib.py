@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.environ.get("R433B_LIB") or os.path.join(CSRC, "libr433b.so")  # override: tuning experiments only
 
-FMT_CU8, FMT_CS16, FMT_CS8 = 2, 4, 0x102
+FMT_CU8, FMT_CS16, FMT_CS8, FMT_CF32 = 2, 4, 0x102, 0x204
 FPDM_CLASSIC, FPDM_MINMAX, FPDM_AUTO = 0, 1, 2
 PACKAGE_OOK, PACKAGE_FSK = 1, 2
 
