@@ -38,6 +38,13 @@ def test_load_batches_groups_and_aligns(tmp_path):
     assert cu8["files"] == [str(pa), str(pb)]
     assert list(cu8["lengths"]) == [a.nbytes, b.nbytes]
     assert all(int(o) % 16 == 0 for o in cu8["offsets"])
+    # cf32: 8 bytes per sample, 32-byte aligned starts (the device turns it into cs16 at half the size)
+    f = (c.astype(np.float32) / np.float32(32768))[: 2 * 1001]
+    pf = tmp_path / "f_868M_1024k.cf32"
+    f.tofile(pf)
+    (fb,) = captures.load_batches([str(pf), str(pf)])
+    assert (fb["format"], fb["abi_format"], fb["sample_rate"]) == ("cf32", lib.FMT_CF32, 1024000)
+    assert list(fb["lengths"]) == [f.nbytes, f.nbytes] and all(int(o) % 32 == 0 for o in fb["offsets"])
     assert bytes(cu8["data"][int(cu8["offsets"][1]):int(cu8["offsets"][1]) + b.nbytes]) == b.tobytes()
 
 
