@@ -71,7 +71,25 @@ for r in csv.reader(io.StringIO(src)):
 ts = sum(v[0] for v in agg.values()) or 1
 ti = sum(v[1] for v in agg.values()) or 1
 lines += ["", "## hottest source lines (stall samples / executed warp instructions)", "", "| samples | instr | where | source |", "|---|---|---|---|"]
+import os  # noqa: E402
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_src_cache = {}
+
+
+def source_text(fn, ln):
+    if fn not in _src_cache:
+        path = os.path.join(ROOT, "rtl_433_b200", "csrc", fn)
+        _src_cache[fn] = open(path).read().split("\n") if os.path.exists(path) else []
+    t = _src_cache[fn]
+    return t[ln - 1].strip()[:100].replace("|", "\\|") if 0 < ln <= len(t) else "-"
+
+
 for (fn, ln), (sm, ins, text) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:25]:
-    lines.append(f"| {100 * sm / ts:.1f}% | {100 * ins / ti:.1f}% | {fn}:{ln} | `{text.strip()[:90]}` |")
+    lines.append(f"| {100 * sm / ts:.1f}% | {100 * ins / ti:.1f}% | {fn}:{ln} | `{source_text(fn, ln)}` |")
+kind = "detect" if "k_detect" in kernel else "slice" if "k_slice" in kernel else None
+if kind:
+    reg = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_regions.py"), rep, kind], capture_output=True, text=True).stdout
+    lines += ["", "## by code region (tools/ncu_regions.py; IQ samples of the 4096 x 2^20 workload)", "", reg.rstrip()]
 open(out_md, "w").write("\n".join(lines) + "\n")
 print("\n".join(lines[:40]))
