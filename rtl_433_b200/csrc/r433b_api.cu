@@ -375,13 +375,19 @@ int r433b_process(r433b_ctx *ctx, r433b_batch const *b)
     };
     std::sort(ook.begin(), ook.end(), by_mod);
     std::sort(fsk.begin(), fsk.end(), by_mod);
-    // one k_slice work item is 32 consecutive list slots: start every modulation on a multiple of
-    // 32 (holes = kNoDevice) so that a warp never runs two slicers one after the other
+    // one k_slice work item is 32 consecutive list slots: start every LARGE modulation (>= 16 devices)
+    // on a multiple of 32 (holes = kNoDevice) so that its warps run one slicer front end only; the
+    // rare modulations share a warp (front ends one after the other, one shared back end) instead
+    // of each costing a whole warp's pass over the pulses for a handful of lanes
     auto align_groups = [&](std::vector<unsigned> &v) {
         std::vector<unsigned> out;
         for (size_t i = 0; i < v.size(); ++i) {
-            if (i && ctx->devs[v[i]].modulation != ctx->devs[v[i - 1]].modulation)
-                while (out.size() % 32) out.push_back(kNoDevice);
+            if (i && ctx->devs[v[i]].modulation != ctx->devs[v[i - 1]].modulation) {
+                size_t n_same = 0;
+                for (size_t j = i; j < v.size() && ctx->devs[v[j]].modulation == ctx->devs[v[i]].modulation; ++j) n_same++;
+                if (n_same >= 16)
+                    while (out.size() % 32) out.push_back(kNoDevice);
+            }
             out.push_back(v[i]);
         }
         v.swap(out);
