@@ -358,42 +358,9 @@ int r433b_process(r433b_ctx *ctx, r433b_batch const *b)
 
     // slicer parameters: per device, scaled to this batch's sample rate on the host
     std::vector<SlicerParams> sp(n_devs);
-    std::vector<unsigned> ook, fsk;
     for (uint32_t i = 0; i < n_devs; ++i) sp[i] = scale_device(ctx->devs[i], b->samp_rate);
-    for (uint32_t i = 0; i < n_devs; ++i) {
-        if (device_takes((int)ctx->devs[i].modulation, 1)) ook.push_back(i);
-        if (device_takes((int)ctx->devs[i].modulation, 2)) fsk.push_back(i);
-    }
-    auto by_mod = [&](unsigned a, unsigned c) {
-        // lanes of a warp should walk the same code: same slicer, then similar event cadence
-        r433b_device const &x = ctx->devs[a], &y = ctx->devs[c];
-        // (measured alternatives: event cadence first 61 ms, registration order 69 ms vs 35 ms)
-        if (x.modulation != y.modulation) return x.modulation < y.modulation;
-        if (x.reset_limit != y.reset_limit) return x.reset_limit < y.reset_limit;
-        if (x.short_width != y.short_width) return x.short_width < y.short_width;
-        return a < c;
-    };
-    std::sort(ook.begin(), ook.end(), by_mod);
-    std::sort(fsk.begin(), fsk.end(), by_mod);
-    // one k_slice work item is 32 consecutive list slots: start every LARGE modulation (>= 16 devices)
-    // on a multiple of 32 (holes = kNoDevice) so that its warps run one slicer front end only; the
-    // rare modulations share a warp (front ends one after the other, one shared back end) instead
-    // of each costing a whole warp's pass over the pulses for a handful of lanes
-    auto align_groups = [&](std::vector<unsigned> &v) {
-        std::vector<unsigned> out;
-        for (size_t i = 0; i < v.size(); ++i) {
-            if (i && ctx->devs[v[i]].modulation != ctx->devs[v[i - 1]].modulation) {
-                size_t n_same = 0;
-                for (size_t j = i; j < v.size() && ctx->devs[v[j]].modulation == ctx->devs[v[i]].modulation; ++j) n_same++;
-                if (n_same >= 16)
-                    while (out.size() % 32) out.push_back(kNoDevice);
-            }
-            out.push_back(v[i]);
-        }
-        v.swap(out);
-    };
-    align_groups(ook);
-    align_groups(fsk);
+    // which devices look at OOK / FSK packages, in the order k_slice's warps take them
+    std::vector<unsigned> ook = slice_list(ctx->devs, 1), fsk = slice_list(ctx->devs, 2);
     ctx->n_ook = (unsigned)ook.size();
     ctx->n_fsk = (unsigned)fsk.size();
     if (int r = dev_reserve(ctx, ctx->d_devparams, std::max<size_t>(1, n_devs) * sizeof(SlicerParams))) return r;

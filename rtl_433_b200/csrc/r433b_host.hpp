@@ -2,9 +2,11 @@
 // driver (tests/host_core.cpp): the float/double parameter derivations the reference does once
 // per run, and the decoder-side re-inflation of compact events into a bitbuffer_t.
 #pragma once
+#include <algorithm>
 #include <cmath>
 #include <cstdint>
 #include <cstring>
+#include <vector>
 
 #include "../../include/r433b.h"
 #include "../../include/r433b_abi.h"
@@ -74,6 +76,40 @@ inline SlicerParams scale_device(r433b_device const &d, uint32_t rate)
     t.f_long = d.long_width > 0.0f ? 1.0f / (d.long_width * per_us) : 0;
     t.priority = d.priority;
     return t;
+}
+
+
+// The device list k_slice walks for one package type (1 = OOK, 2 = FSK): indices into `devs` of the
+// devices run_ook_demods / run_fsk_demods hand such a package to (src/r_api.c:438-550), ordered so
+// that the 32 lanes of a warp walk the same code -- same slicer, then similar event cadence (reset
+// limit, short width; measured alternatives: event cadence first 61 ms, registration order 69 ms vs
+// 35 ms).  One k_slice work item is 32 consecutive slots: every LARGE modulation (>= 16 devices)
+// starts on a multiple of 32 (holes = kNoDevice) so that its warps run one slicer front end only;
+// the rare modulations share a warp (front ends one after the other, one shared back end) instead of
+// each costing a whole warp's pass over the pulses for a handful of lanes.
+inline std::vector<unsigned> slice_list(std::vector<r433b_device> const &devs, int package_type)
+{
+    std::vector<unsigned> v;
+    for (unsigned i = 0; i < (unsigned)devs.size(); ++i)
+        if (device_takes((int)devs[i].modulation, package_type)) v.push_back(i);
+    std::sort(v.begin(), v.end(), [&](unsigned a, unsigned c) {
+        r433b_device const &x = devs[a], &y = devs[c];
+        if (x.modulation != y.modulation) return x.modulation < y.modulation;
+        if (x.reset_limit != y.reset_limit) return x.reset_limit < y.reset_limit;
+        if (x.short_width != y.short_width) return x.short_width < y.short_width;
+        return a < c;
+    });
+    std::vector<unsigned> out;
+    for (size_t i = 0; i < v.size(); ++i) {
+        if (i && devs[v[i]].modulation != devs[v[i - 1]].modulation) {
+            size_t n_same = 0;
+            for (size_t j = i; j < v.size() && devs[v[j]].modulation == devs[v[i]].modulation; ++j) n_same++;
+            if (n_same >= 16)
+                while (out.size() % 32) out.push_back(kNoDevice);
+        }
+        out.push_back(v[i]);
+    }
+    return out;
 }
 
 

@@ -1136,7 +1136,6 @@ struct SliceParams {
 };
 
 constexpr int kSliceThreads = 128;
-constexpr unsigned kNoDevice = 0xffffffffu; // hole in a device list (alignment padding)
 constexpr unsigned kStageWords = 1024; // scratch words per k_slice thread (4 KiB): larger outputs take the second pass
 constexpr int kSliceCtasPerSm = 12; // 40 registers, 48 warps/SM (measured: 8 -> 13.3 ms, 10 -> 12.4, 12 -> 12.2, 16 -> 13.4)
 

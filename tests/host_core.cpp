@@ -350,6 +350,14 @@ int16_t const *hc_am(void *p) { return ((Hc *)p)->am.data(); }
 int16_t const *hc_fm(void *p) { return ((Hc *)p)->fm.data(); }
 
 
+// the device list k_slice walks for one package type (rtl_433_b200/csrc/r433b_host.hpp: slice_list)
+int hc_slice_list(void *p, int package_type, uint32_t *out, int cap)
+{
+    std::vector<unsigned> v = slice_list(((Hc *)p)->devs, package_type);
+    for (int i = 0; i < (int)v.size() && i < cap; ++i) out[i] = v[(size_t)i];
+    return (int)v.size();
+}
+
 // ---- invariants the warp-level kernel code relies on, checked on the product's own functions ----
 
 // k_detect's PULSE fast path: one step of the high-level estimator never lifts it above

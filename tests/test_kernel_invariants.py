@@ -3,7 +3,10 @@ the two invariants the warp-level shortcuts of k_detect rest on; the shortcuts t
 covered bit-for-bit by the -m gpu parity tests."""
 import ctypes as C
 
+import numpy as np
+
 import helpers
+from rtl_433_b200 import lib
 
 
 def _lib():
@@ -31,3 +34,33 @@ def test_fm_filter_state_rebuild_is_sound_and_usually_converges():
         assert n >= 0
     # constant input: the floor map keeps distinct fixed points apart for at least some levels
     assert L.hc_check_bracket_rebuild(9, 200, 0, 250000, 1024, 0) < 200
+
+
+def test_slice_work_lists_cover_every_device_once_and_align_large_modulations():
+    """k_slice's work items are 32 consecutive slots of these lists: every device that takes the
+    package type appears exactly once, holes are padding only, a modulation with >= 16 devices
+    starts on a warp boundary, and devices of one modulation stay together."""
+    devs = lib.default_device_table(include_disabled=True)
+    hc = helpers.HostCore()
+    hc.add_devices(devs)
+    hc.L.hc_slice_list.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+    for ptype, takes in ((1, lambda m: 3 <= m <= 13 and m != 7), (2, lambda m: 16 <= m <= 18)):
+        buf = np.zeros(4096, np.uint32)
+        n = hc.L.hc_slice_list(hc.h, ptype, buf.ctypes.data, len(buf))
+        lst = buf[:n]
+        real = [int(x) for x in lst if x != 0xFFFFFFFF]
+        want = [i for i, d in enumerate(devs) if takes(d["modulation"])]
+        assert sorted(real) == want
+        mods = [devs[i]["modulation"] for i in real]
+        assert mods == sorted(mods), "devices of one modulation are contiguous, modulations ascending"
+        count = {m: mods.count(m) for m in set(mods)}
+        seen = set()
+        for slot, x in enumerate(lst):
+            if x == 0xFFFFFFFF:
+                continue
+            m = devs[int(x)]["modulation"]
+            if m not in seen:
+                seen.add(m)
+                if count[m] >= 16:
+                    assert slot % 32 == 0, f"modulation {m} ({count[m]} devices) starts at slot {slot}"
+        assert n - len(real) < 32 * len(count)
