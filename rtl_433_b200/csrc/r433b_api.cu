@@ -49,6 +49,8 @@ struct r433b_ctx {
     bool processed = false, fetched = false;
     unsigned fpdm = 0;
     int enable_fm = 0;
+    int n_sms = 148;        // cudaDevAttrMultiProcessorCount of `device`
+    unsigned stage_words = kStageWords; // R433B_STAGE_WORDS overrides (tuning experiments)
     int lazy_fm = 1; // R433B_EAGER_FM=1 in the environment turns the on-demand FM path off (A/B checks)
     Levels lv{};
     // device memory (grow only)
@@ -152,6 +154,9 @@ int r433b_create(int cuda_device, r433b_ctx **out)
     cudaEventCreateWithFlags(&ctx->ev_init, cudaEventDisableTiming);
     ctx->lv = compute_levels(0, 0.0f, -12.1442f, 9.0f);
     if (char const *v = getenv("R433B_EAGER_FM")) ctx->lazy_fm = !(v[0] && v[0] != '0');
+    if (char const *v = getenv("R433B_STAGE_WORDS")) ctx->stage_words = (unsigned)std::max(8, atoi(v));
+    if (cudaDeviceGetAttribute(&ctx->n_sms, cudaDevAttrMultiProcessorCount, cuda_device) != cudaSuccess || ctx->n_sms <= 0)
+        ctx->n_sms = 148;
     *out = ctx;
     return R433B_OK;
 }
@@ -374,6 +379,7 @@ int r433b_process(r433b_ctx *ctx, r433b_batch const *b)
     if (ctx->pool_cap < ctx->pkg_cap * 128) ctx->pool_cap = ctx->pkg_cap * 128;
     if (ctx->arena_cap < total_bytes / 2 + (1u << 20)) ctx->arena_cap = total_bytes / 2 + (1u << 20);
 
+    unsigned stage_words = 0; // set below, before the first fill_slice() call
     auto fill_slice = [&](SliceParams &q) {
         q.pkgs = (r433b_package *)ctx->d_pkgs.p;
         q.range = nullptr;
@@ -390,12 +396,13 @@ int r433b_process(r433b_ctx *ctx, r433b_batch const *b)
         q.arena_cap = ctx->arena_cap;
         q.cursor = (unsigned long long *)ctx->d_cursor.p;
         q.stage = (uint32_t *)ctx->d_stage.p;
-        q.stage_words = kStageWords;
+        q.stage_words = stage_words;
     };
     // k_slice always runs as a fixed grid whose CTAs fetch packages (GroupRange::next): every thread
     // of that grid owns kStageWords of scratch for the staged single pass
-    unsigned const slice_grid = 148 * kSliceCtasPerSm;
-    if (int r = dev_reserve(ctx, ctx->d_stage, (size_t)slice_grid * kSliceThreads * kStageWords * sizeof(uint32_t))) return r;
+    unsigned const slice_grid = (unsigned)ctx->n_sms * kSliceCtasPerSm;
+    stage_words = ctx->stage_words;
+    if (int r = dev_reserve(ctx, ctx->d_stage, (size_t)slice_grid * kSliceThreads * stage_words * sizeof(uint32_t))) return r;
 
     // ---- pipelined path: host input cut into G TIME SLICES of every stream; the copy-in of slice
     //      k+1 and the copy-out of finished ranges overlap the kernels of slice k (three streams).
@@ -447,6 +454,10 @@ int r433b_process(r433b_ctx *ctx, r433b_batch const *b)
         unsigned const *d_cnt = (unsigned const *)ctx->d_counters.p;
         unsigned long long const *d_cur = (unsigned long long const *)ctx->d_cursor.p;
 
+        // the table uploads above went through the legacy stream from pageable memory: their DMA may still be
+        // in flight when cudaMemcpy returns, and s_det does not synchronise with stream 0 by itself
+        CU(cudaEventRecord(ctx->ev_init, 0));
+        CU(cudaStreamWaitEvent(ctx->s_det, ctx->ev_init, 0));
         CU(cudaMemsetAsync(ctx->d_counters.p, 0, 64, ctx->s_det));
         CU(cudaMemsetAsync(ctx->d_cursor.p, 0, 64, ctx->s_det));
         CU(cudaMemsetAsync(ctx->d_pairs.p, 0, pair_cap_bytes, ctx->s_det));
@@ -491,8 +502,9 @@ int r433b_process(r433b_ctx *ctx, r433b_batch const *b)
             if (overflow) continue;
             size_t pk_hi = (size_t)r.pkg_end * sizeof(r433b_package), pool_hi = (size_t)r.pool_end * sizeof(int);
             size_t pair_hi = (size_t)r.pkg_end * n_devs * sizeof(r433b_pair);
-            if (ctx->h_pkgs.cap < pk_hi || ctx->h_ppool.cap < pool_hi || ctx->h_gpool.cap < pool_hi || ctx->h_pairs.cap < pair_hi
-                    || ctx->h_events.cap < r.arena_end)
+            // the same sizes r433b_fetch() reserves (+16): a buffer that passes here is never reallocated there
+            if (ctx->h_pkgs.cap < pk_hi + 16 || ctx->h_ppool.cap < pool_hi + 16 || ctx->h_gpool.cap < pool_hi + 16
+                    || ctx->h_pairs.cap < pair_hi + 16 || ctx->h_events.cap < r.arena_end + 16)
                 d2h_ok = false;
             if (!d2h_ok) continue;
             size_t pk_lo = (size_t)r.pkg_begin * sizeof(r433b_package), pool_lo = (size_t)r.pool_begin * sizeof(int);
@@ -510,6 +522,8 @@ int r433b_process(r433b_ctx *ctx, r433b_batch const *b)
         CU(cudaStreamSynchronize(ctx->s_out));
         if (!overflow) {
             GroupRange const last = h_rg[G - 1];
+            if ((uint64_t)last.pkg_end * n_devs > 0xffffffffull)
+                return fail(ctx, R433B_EOVERFLOW, "packages x devices exceeds the 32-bit pair index (r433b_package.first_pair)");
             ctx->n_pkgs = last.pkg_end;
             ctx->pool_used = last.pool_end;
             ctx->event_bytes = last.arena_end;
@@ -553,7 +567,7 @@ int r433b_process(r433b_ctx *ctx, r433b_batch const *b)
             raw = ctx->d_raw.p;
         }
         size_t n4 = (size_t)(2 * total_bytes / 16); // groups of four floats (offsets are multiples of 32 bytes)
-        k_cf32_to_cs16<<<148 * 8, 256, 0, st>>>((float4 const *)raw, (uint2 *)ctx->d_data.p, n4);
+        k_cf32_to_cs16<<<ctx->n_sms * 8, 256, 0, st>>>((float4 const *)raw, (uint2 *)ctx->d_data.p, n4);
         CU(cudaGetLastError());
     } else if (!b->data_on_device && total_bytes)
         CU(cudaMemcpyAsync(ctx->d_data.p, b->data, total_bytes, cudaMemcpyHostToDevice, st));
@@ -584,6 +598,8 @@ int r433b_process(r433b_ctx *ctx, r433b_batch const *b)
         ctx->pool_cap = std::max<size_t>(ctx->pool_cap, (size_t)counters[1] + 4096);
         if (attempt == 2) return fail(ctx, R433B_EOVERFLOW, "package arena overflow");
     }
+    if ((uint64_t)counters[0] * n_devs > 0xffffffffull)
+        return fail(ctx, R433B_EOVERFLOW, "packages x devices exceeds the 32-bit pair index (r433b_package.first_pair)");
     ctx->n_pkgs = counters[0];
     ctx->pool_used = counters[1];
     CU(cudaEventRecord(ctx->ev[2], st));

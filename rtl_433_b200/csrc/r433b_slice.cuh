@@ -51,7 +51,8 @@ constexpr unsigned kNoDevice = 0xffffffffu; // hole in a k_slice device list (al
 
 struct SlicerParams {
     int modulation;
-    int ok; // 0: "sample rate too low" -> the slicer returns without events
+    int ok; // bit 0: all six scaled widths survived (the check of every slicer but RZI, src/pulse_slicer.c:79-84);
+            // bit 1: short/long/reset survived (RZI's check, :877-879).  A clear bit = "sample rate too low": no events
     int s_short, s_long, s_reset, s_gap, s_sync, s_tol;
     float f_short, f_long; // 1/(width*samples_per_us) or 0
     unsigned priority;
@@ -309,7 +310,7 @@ R4_HD bool slicer_begin(PulseView const &p, SlicerParams const &t, SlicerState &
     int const big = 0x7fffffff;
     switch (t.modulation) {
     case kModOokPwm: case kModFskPwm: { // src/pulse_slicer.c:369-413; b0..b5 = one/zero/sync lo,hi
-        if (!t.ok) return false;
+        if (!(t.ok & 1)) return false;
         st.b4 = st.b5 = 0;
         if (t.s_tol > 0) {
             st.b0 = t.s_short - t.s_tol; st.b1 = t.s_short + t.s_tol;
@@ -334,7 +335,7 @@ R4_HD bool slicer_begin(PulseView const &p, SlicerParams const &t, SlicerState &
         return true;
     }
     case kModOokPpm: { // :291-308; b0..b5 = zero/one/sync lo,hi
-        if (!t.ok) return false;
+        if (!(t.ok & 1)) return false;
         st.b4 = st.b5 = 0;
         if (t.s_tol > 0) {
             st.b0 = t.s_short - t.s_tol; st.b1 = t.s_short + t.s_tol;
@@ -349,7 +350,7 @@ R4_HD bool slicer_begin(PulseView const &p, SlicerParams const &t, SlicerState &
         return true;
     }
     case kModOokPcm: case kModFskPcm: { // :89-214, the bit-period estimators
-        if (!t.ok || t.s_long == 0) return false;
+        if (!(t.ok & 1) || t.s_long == 0) return false;
         float f_short = t.f_short, f_long = t.f_long;
         int const gap_limit = t.s_gap ? t.s_gap : t.s_reset;
         int tol = t.s_tol;
@@ -422,20 +423,20 @@ R4_HD bool slicer_begin(PulseView const &p, SlicerParams const &t, SlicerState &
         return true;
     }
     case kModOokMc: case kModFskMc: // :451-478
-        if (!t.ok) return false;
+        if (!(t.ok & 1)) return false;
         st.edge = dmul((double)t.s_short, 1.5);
         st.i0 = t.s_short - t.s_tol;
         st.i1 = t.s_short * 2 + t.s_tol;
         st.pending = true; // "First rising edge is always counted as a zero"
         return true;
     case kModOokDmc: case kModOokPiwmRaw: case kModOokPiwmDc:
-        if (!t.ok) return false;
+        if (!(t.ok & 1)) return false;
         st.total = p.n * 2;
         return true;
     case kModOokNrzs:
-        return t.ok && t.s_short != 0;
+        return (t.ok & 1) && t.s_short != 0;
     case kModOokOsv1: { // :797-835: twelve preamble pulses, a sync, then manchester data
-        if (!t.ok) return false;
+        if (!(t.ok & 1)) return false;
         int const half_lo = t.s_short / 2, half_hi = t.s_short * 3 / 2, sync_lo = 2 * half_hi;
         int pre = 0;
         unsigned n;

@@ -211,3 +211,59 @@ def fsk_stream(seed, n_samples=1 << 20, rate=FSK_RATE, n_bursts=4, sigma=40.0, b
         x[2 * pos + 1:2 * (pos + blen) + 1:2] += amp * np.sin(ph).astype(np.float32)
         pos += blen
     return np.clip(np.rint(x), -32767, 32767).astype(np.int16)
+
+
+def ook_train_stream(seed, n_pulses, on_us=200.0, off_us=200.0, n_samples=1 << 19, rate=OOK_RATE, sigma=2.0,
+                     jitter_us=0.0, lead_us=8000.0):
+    """cu8 IQ with ONE long on/off keyed train of `n_pulses` pulses (more than PD_MAX_PULSES = 1200 makes the
+    detector return a full package mid-train, src/pulse_detect.c:429-441) over a noise floor."""
+    rng = np.random.default_rng(seed)
+    x = rng.standard_normal(2 * n_samples, dtype=np.float32) * np.float32(sigma) + np.float32(127.5)
+    seg = []
+    for _ in range(n_pulses):
+        seg.append((on_us + (rng.uniform(-jitter_us, jitter_us) if jitter_us else 0.0), 1))
+        seg.append((off_us + (rng.uniform(-jitter_us, jitter_us) if jitter_us else 0.0), 0))
+    m = _render_ook(seg, rate)
+    pos = int(lead_us * rate / 1e6)
+    if pos + len(m) + int(0.02 * rate) > n_samples:
+        raise ValueError("stream too short for the requested train")
+    amp = np.float32(rng.uniform(60, 110))
+    f = rng.uniform(-40e3, 40e3)
+    ph = rng.uniform(0, 2 * np.pi) + 2 * np.pi * f / rate * np.arange(len(m), dtype=np.float64)
+    on = m.astype(np.float32) * amp
+    x[2 * pos:2 * (pos + len(m)):2] += on * np.cos(ph).astype(np.float32)
+    x[2 * pos + 1:2 * (pos + len(m)) + 1:2] += on * np.sin(ph).astype(np.float32)
+    return np.clip(np.rint(x), 0, 255).astype(np.uint8)
+
+
+def cu8_to_cs16(x, gain=96):
+    """The same capture as a cs16 file would hold it: (v - 128) * gain (|gain| <= 256 keeps it inside int16)."""
+    return ((x.astype(np.int16) - 128) * np.int16(gain)).astype(np.int16)
+
+
+def fsk_burst_stream(seed, n_bits, bit_us=100.0, n_samples=1 << 19, rate=FSK_RATE, sigma=40.0, dev_hz=40e3, cu8=False,
+                     alternate=True, lead_us=8000.0):
+    """ONE 2-FSK burst of `n_bits` bits (alternating by default: one frequency transition per bit, so more than
+    2 x 1200 bits overflow the FSK pulse train and exercise pulse_data_shift, src/pulse_detect_fsk.c:114,205).
+    cs16 by default; cu8=True renders the same burst as unsigned 8-bit IQ (amplitude 100 LSB, sigma 2)."""
+    rng = np.random.default_rng(seed)
+    spb = bit_us * rate / 1e6
+    blen = int(np.ceil(n_bits * spb))
+    pos = int(lead_us * rate / 1e6)
+    if pos + blen + int(0.02 * rate) > n_samples:
+        raise ValueError("stream too short for the requested burst")
+    bits = np.tile([1, 0], (n_bits + 1) // 2)[:n_bits] if alternate else rng.integers(0, 2, n_bits)
+    idx = np.minimum((np.arange(blen) / spb).astype(np.int64), n_bits - 1)
+    freq = np.where(bits[idx] > 0, dev_hz, -dev_hz) + rng.uniform(-10e3, 10e3)
+    ph = rng.uniform(0, 2 * np.pi) + 2 * np.pi * np.cumsum(freq) / rate
+    if cu8:
+        x = rng.standard_normal(2 * n_samples, dtype=np.float32) * np.float32(2.0) + np.float32(127.5)
+        amp = np.float32(100.0)
+    else:
+        x = rng.standard_normal(2 * n_samples, dtype=np.float32) * np.float32(sigma)
+        amp = np.float32(rng.uniform(4000, 14000))
+    x[2 * pos:2 * (pos + blen):2] += amp * np.cos(ph).astype(np.float32)
+    x[2 * pos + 1:2 * (pos + blen) + 1:2] += amp * np.sin(ph).astype(np.float32)
+    if cu8:
+        return np.clip(np.rint(x), 0, 255).astype(np.uint8)
+    return np.clip(np.rint(x), -32767, 32767).astype(np.int16)

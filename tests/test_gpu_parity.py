@@ -259,3 +259,106 @@ def test_priority_classes_stop_after_a_decode(ctx):
         assert order == sorted(order, key=lambda d: (devs[d].get("priority", 0), d))
     finally:
         c.close()
+
+
+def fresh_ctx(devs):
+    c = lib.Context(0)
+    c.set_devices(devs)
+    return c
+
+
+def test_custom_piwm_raw_and_nrzs_devices():
+    """pulse_slicer_piwm_raw / pulse_slicer_nrzs (src/pulse_slicer.c:597-657, :715-759) have no default-enabled
+    device: hand-made devices of every modulation (tests/test_parity_holes.py pins the oracle on the same set)."""
+    from test_parity_holes import MOD, custom_devices
+    devs = custom_devices()
+    c = fresh_ctx(devs)
+    try:
+        o = oracle_for(devs)
+        streams = [synth.ook_stream(71, n_samples=1 << 19, n_bursts=5), synth.ook_stream(73, n_samples=1 << 19, n_bursts=5)]
+        gpu = run_gpu(c, streams, lib.FMT_CU8, 250000, 433920000)
+        seen = set()
+        for i, s in enumerate(streams):
+            ref = o.run(s, 2)
+            seen |= {devs[e["dev"]]["modulation"] for e in ref["events"]}
+            check(gpu[i], ref, f"custom ook {i}")
+        assert {MOD["OOK_PIWM_RAW"], MOD["OOK_NRZS"]} <= seen
+        streams = [synth.fsk_stream(72, n_samples=1 << 18, n_bursts=2)]
+        gpu = run_gpu(c, streams, lib.FMT_CS16, 1024000, 868000000)
+        check(gpu[0], o.run(streams[0], 4, 1024000, 868000000), "custom fsk")
+        # a rate at which single widths truncate to zero samples: the six-field check must silence those devices
+        streams = [synth.ook_stream(74, n_samples=1 << 17, rate=48000, n_bursts=2, kinds=("nice", "manchester"))]
+        gpu = run_gpu(c, streams, lib.FMT_CU8, 48000, 433920000)
+        check(gpu[0], o.run(streams[0], 2, 48000, 433920000), "custom 48 kS/s")
+    finally:
+        c.close()
+
+
+def test_all_protocols_including_disabled():
+    """All 384 protocols (klimalogg = NRZS; 198 / 270: tolerance 1 us -> 0 samples at 250 kS/s, the reference's
+    'sample rate too low' return, src/pulse_slicer.c:79-84)."""
+    devs = lib.default_device_table(include_disabled=True)
+    assert len(devs) >= 380
+    c = fresh_ctx(devs)
+    try:
+        o = oracle_for(devs)
+        streams = [synth.ook_stream(81, n_samples=1 << 19, n_bursts=4), synth.ook_stream(82, n_samples=1 << 19, n_bursts=4)]
+        gpu = run_gpu(c, streams, lib.FMT_CU8, 250000, 433920000)
+        for i, s in enumerate(streams):
+            check(gpu[i], o.run(s, 2), f"all protocols {i}")
+    finally:
+        c.close()
+
+
+def test_ook_1200_pulse_end_of_package(ctx, devices):
+    """PD_MAX_PULSES reached inside a train (src/pulse_detect.c:429-441): through det_step() and through the
+    GAP scan's own copy of that branch; different phases of the train against the tile grid."""
+    streams = [synth.ook_train_stream(1, 1300, 200.0, 200.0), synth.ook_train_stream(2, 2500, 120.0, 80.0),
+               synth.ook_train_stream(5, 1201, 400.0, 60.0), synth.ook_train_stream(3, 1201, 400.0, 44.0),
+               synth.ook_train_stream(6, 1250, 180.0, 1900.0, n_samples=1 << 20, lead_us=9137.0)]
+    gpu = run_gpu(ctx, streams, lib.FMT_CU8, 250000, 433920000)
+    o = oracle_for(devices)
+    for i, s in enumerate(streams):
+        ref = o.run(s, 2)
+        if i != 3:
+            assert [p["num_pulses"] for p in ref["packages"] if p["type"] == 1][0] == 1200
+        check(gpu[i], ref, f"ook train {i}")
+
+
+def test_fsk_train_overflow_shifts_the_pulse_train(ctx, devices):
+    """> 1200 FSK pulses in one carrier: pulse_data_shift and its `offset += 600` (src/pulse_data.c:27-34,
+    src/pulse_detect_fsk.c:114, :205), classic and minmax detectors, cs16 and cu8 captures."""
+    o = oracle_for(devices)
+    streams = [synth.fsk_burst_stream(2, 2700), synth.fsk_burst_stream(5, 3900, bit_us=60.0)]
+    for fpdm, freq in ((lib.FPDM_AUTO, 868000000), (lib.FPDM_CLASSIC, 433920000)):
+        gpu = run_gpu(ctx, streams, lib.FMT_CS16, 1024000, freq, fpdm)
+        for i, s in enumerate(streams):
+            ref = o.run(s, 4, 1024000, freq, fpdm)
+            assert any(p["type"] == 2 and p["num_pulses"] >= 600 for p in ref["packages"])
+            check(gpu[i], ref, f"fsk overflow {i} fpdm {fpdm}")
+    streams = [synth.fsk_burst_stream(7, 2600, bit_us=200.0, n_samples=1 << 18, rate=250000, cu8=True, dev_hz=30e3)]
+    for freq in (868000000, 433920000):
+        gpu = run_gpu(ctx, streams, lib.FMT_CU8, 250000, freq)
+        ref = o.run(streams[0], 2, 250000, freq)
+        assert any(p["type"] == 2 and p["num_pulses"] >= 600 for p in ref["packages"])
+        check(gpu[0], ref, f"fsk overflow cu8 {freq}")
+
+
+def test_rates_and_formats_round_1_never_compared(ctx, devices):
+    """2.048 MS/s cu8, OOK in cs16 captures (two rates), FSK packages out of a cu8 capture (both detectors)."""
+    o = oracle_for(devices)
+    streams = [synth.ook_stream(61, n_samples=1 << 20, rate=2048000, n_bursts=4, kinds=("nice", "manchester"))]
+    gpu = run_gpu(ctx, streams, lib.FMT_CU8, 2048000, 433920000)
+    check(gpu[0], o.run(streams[0], 2, 2048000, 433920000), "2.048 MS/s cu8")
+    streams = [synth.cu8_to_cs16(synth.ook_stream(62, n_samples=1 << 19, rate=1024000, n_bursts=3, kinds=("nice", "manchester")))]
+    gpu = run_gpu(ctx, streams, lib.FMT_CS16, 1024000, 433920000)
+    check(gpu[0], o.run(streams[0], 4, 1024000, 433920000), "cs16 OOK 1.024 MS/s")
+    streams = [synth.cu8_to_cs16(synth.ook_stream(63, n_samples=1 << 18, n_bursts=3, kinds=("nice", "manchester", "silvercrest")), gain=200)]
+    gpu = run_gpu(ctx, streams, lib.FMT_CS16, 250000, 433920000)
+    check(gpu[0], o.run(streams[0], 4, 250000, 433920000), "cs16 OOK 250 kS/s")
+    streams = [synth.fsk_burst_stream(64, 600, bit_us=400.0, n_samples=1 << 18, rate=250000, cu8=True, dev_hz=30e3)]
+    for freq in (433920000, 868000000):
+        gpu = run_gpu(ctx, streams, lib.FMT_CU8, 250000, freq)
+        ref = o.run(streams[0], 2, 250000, freq)
+        assert any(p["type"] == 2 for p in ref["packages"])
+        check(gpu[0], ref, f"cu8 FSK {freq}")
