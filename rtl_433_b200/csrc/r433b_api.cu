@@ -17,6 +17,15 @@
 
 using namespace r433b;
 
+// Kernel launches go through one macro so that the tests can build this translation unit against the SIMT
+// emulator (tests/simt/): there the same kernels run one fibre per CUDA thread on the CPU.  The product build
+// (nvcc, no R433B_SIMT_EMU) is always the <<< >>> form.
+#ifdef R433B_SIMT_EMU
+#define R4_LAUNCH(kernel, grid, block, smem, stream, ...) simt::launch(dim3(grid), dim3(block), (size_t)(smem), kernel, __VA_ARGS__)
+#else
+#define R4_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+#endif
+
 static_assert(sizeof(struct bitbuffer) == 6604, "bitbuffer_t layout");
 static_assert(sizeof(struct pulse_data) == 9672, "pulse_data_t layout");
 static_assert(sizeof(struct r_device) == 152, "r_device layout");
@@ -70,7 +79,7 @@ struct r433b_ctx {
     cudaStream_t s_in = nullptr, s_det = nullptr, s_out = nullptr;
     static constexpr int kMaxGroups = 16;
     cudaEvent_t ev_in[kMaxGroups]{}, ev_det[kMaxGroups]{}, ev_slc[kMaxGroups]{}, ev_t[4 * kMaxGroups]{}, ev_init = nullptr;
-    DevBuf d_ranges, d_state, d_lengths, d_stage, d_raw;
+    DevBuf d_ranges, d_state, d_lengths, d_stage, d_raw, d_log;
     HostBuf h_ranges;
     bool d2h_done = false;
 };
@@ -167,7 +176,7 @@ void r433b_destroy(r433b_ctx *ctx)
     cudaSetDevice(ctx->device);
     for (DevBuf *b : {&ctx->d_data, &ctx->d_offsets, &ctx->d_train, &ctx->d_pkgs, &ctx->d_ppool, &ctx->d_gpool,
                  &ctx->d_counters, &ctx->d_am, &ctx->d_fm, &ctx->d_devparams, &ctx->d_lists, &ctx->d_pairs,
-                 &ctx->d_arena, &ctx->d_cursor, &ctx->d_ranges, &ctx->d_state, &ctx->d_lengths, &ctx->d_stage, &ctx->d_raw})
+                 &ctx->d_arena, &ctx->d_cursor, &ctx->d_ranges, &ctx->d_state, &ctx->d_lengths, &ctx->d_stage, &ctx->d_raw, &ctx->d_log})
         if (b->p) cudaFree(b->p);
     for (HostBuf *b : {&ctx->h_pkgs, &ctx->h_ppool, &ctx->h_gpool, &ctx->h_pairs, &ctx->h_events, &ctx->h_ranges})
         if (b->p) cudaFreeHost(b->p);
@@ -250,8 +259,8 @@ int r433b_process(r433b_ctx *ctx, r433b_batch const *b)
     if (b->samp_rate == 0) return fail(ctx, R433B_EINVAL, "samp_rate is 0");
     int const SS = (int)(b->sample_format & 0xff); // bytes per IQ sample; cs8 is cu8 after the load-time +128
     uint32_t block_bytes = b->block_bytes ? b->block_bytes : 262144u;
-    int const T = SS == 2 ? TileCfg<2>::T : TileCfg<4>::T;
-    if (block_bytes % (uint32_t)(T * SS) != 0) return fail(ctx, R433B_EINVAL, "block_bytes must be a multiple of 2048");
+    int const T = kTile;
+    if (block_bytes % (uint32_t)(T * SS) != 0) return fail(ctx, R433B_EINVAL, "block_bytes must be a multiple of 2048 samples (4096 bytes of cu8, 8192 of cs16)");
     for (uint32_t i = 0; i <= b->n_streams; ++i) {
         if (b->offsets[i] % (16 * in_div)) return fail(ctx, R433B_EINVAL, "stream offsets must be multiples of 16 bytes (32 for cf32)");
         if (i && b->offsets[i] < b->offsets[i - 1]) return fail(ctx, R433B_EINVAL, "offsets not ascending");
@@ -301,6 +310,7 @@ int r433b_process(r433b_ctx *ctx, r433b_batch const *b)
     if (int r = dev_reserve(ctx, ctx->d_lengths, std::max<size_t>(1, b->n_streams) * sizeof(uint64_t))) return r;
     if (b->n_streams) CU(cudaMemcpy(ctx->d_lengths.p, ctx->lengths.data(), b->n_streams * sizeof(uint64_t), cudaMemcpyHostToDevice));
     if (int r = dev_reserve(ctx, ctx->d_train, (size_t)std::max(1u, b->n_streams) * kTrainInts * sizeof(int))) return r;
+    if (int r = dev_reserve(ctx, ctx->d_log, (size_t)std::max(1u, b->n_streams) * kLogCap * 2 * sizeof(unsigned))) return r;
     if (int r = dev_reserve(ctx, ctx->d_counters, 64)) return r;
     if (int r = dev_reserve(ctx, ctx->d_cursor, 64)) return r;
     if (b->want_stages) {
@@ -338,6 +348,7 @@ int r433b_process(r433b_ctx *ctx, r433b_batch const *b)
         dp.wrap_free = dp.fm_a1 >= 0 && dp.fm_b0 >= 0 && (long long)dp.fm_a1 + 2ll * dp.fm_b0 <= unity;
     }
     dp.train_scratch = (int *)ctx->d_train.p;
+    dp.log_scratch = (unsigned *)ctx->d_log.p;
     dp.counters = (unsigned *)ctx->d_counters.p;
     dp.am_out = b->want_stages ? (int16_t *)ctx->d_am.p : nullptr;
     dp.fm_out = b->want_stages ? (int16_t *)ctx->d_fm.p : nullptr;
@@ -346,19 +357,9 @@ int r433b_process(r433b_ctx *ctx, r433b_batch const *b)
         unsigned n = q.stream_end - q.stream0;
         if (!n) return;
         unsigned grid = (n + kDetectWarps - 1) / kDetectWarps;
-        if (SS == 2) {
-            size_t sm = (size_t)kDetectWarps * TileCfg<2>::kTileWords * sizeof(uint32_t);
-            if (q.wrap_free)
-                k_detect<2, true><<<grid, kDetectWarps * 32, sm, s>>>(q);
-            else
-                k_detect<2, false><<<grid, kDetectWarps * 32, sm, s>>>(q);
-        } else {
-            size_t sm = (size_t)kDetectWarps * TileCfg<4>::kTileWords * sizeof(uint32_t);
-            if (q.wrap_free)
-                k_detect<4, true><<<grid, kDetectWarps * 32, sm, s>>>(q);
-            else
-                k_detect<4, false><<<grid, kDetectWarps * 32, sm, s>>>(q);
-        }
+        size_t sm = (size_t)kDetectWarps * sizeof(WarpSmem);
+        void (*kfn)(DetectParams) = SS == 2 ? k_detect<2> : k_detect<4>;
+        R4_LAUNCH(kfn, grid, kDetectWarps * 32, sm, s, q);
     };
 
     // slicer parameters: per device, scaled to this batch's sample rate on the host
@@ -471,7 +472,7 @@ int r433b_process(r433b_ctx *ctx, r433b_batch const *b)
                         cudaMemcpyHostToDevice, ctx->s_in));
             CU(cudaEventRecord(ctx->ev_in[g], ctx->s_in));
             CU(cudaStreamWaitEvent(ctx->s_det, ctx->ev_in[g], 0));
-            k_mark<<<1, 1, 0, ctx->s_det>>>(d_rg + g, 0, d_cnt, d_cur);
+            R4_LAUNCH(k_mark, 1, 1, 0, ctx->s_det, d_rg + g, 0, d_cnt, d_cur);
             CU(cudaEventRecord(ctx->ev_t[4 * g + 0], ctx->s_det));
             DetectParams dg = dp;
             dg.sample_begin = (uint64_t)g * slice_samples;
@@ -479,15 +480,15 @@ int r433b_process(r433b_ctx *ctx, r433b_batch const *b)
             dg.first_chunk = g == 0;
             launch_detect(dg, ctx->s_det);
             CU(cudaEventRecord(ctx->ev_t[4 * g + 1], ctx->s_det));
-            k_mark<<<1, 1, 0, ctx->s_det>>>(d_rg + g, 1, d_cnt, d_cur);
+            R4_LAUNCH(k_mark, 1, 1, 0, ctx->s_det, d_rg + g, 1, d_cnt, d_cur);
             CU(cudaEventRecord(ctx->ev_det[g], ctx->s_det));
-            k_mark<<<1, 1, 0, ctx->s_det>>>(d_rg + g, 2, d_cnt, d_cur);
+            R4_LAUNCH(k_mark, 1, 1, 0, ctx->s_det, d_rg + g, 2, d_cnt, d_cur);
             CU(cudaEventRecord(ctx->ev_t[4 * g + 2], ctx->s_det));
             SliceParams qg = q;
             qg.range = d_rg + g;
-            k_slice<<<slice_grid, kSliceThreads, 0, ctx->s_det>>>(qg);
+            R4_LAUNCH(k_slice, slice_grid, kSliceThreads, 0, ctx->s_det, qg);
             CU(cudaEventRecord(ctx->ev_t[4 * g + 3], ctx->s_det));
-            k_mark<<<1, 1, 0, ctx->s_det>>>(d_rg + g, 3, d_cnt, d_cur);
+            R4_LAUNCH(k_mark, 1, 1, 0, ctx->s_det, d_rg + g, 3, d_cnt, d_cur);
             CU(cudaMemcpyAsync(h_rg + g, d_rg + g, sizeof(GroupRange), cudaMemcpyDeviceToHost, ctx->s_det));
             CU(cudaEventRecord(ctx->ev_slc[g], ctx->s_det));
         }
@@ -567,7 +568,7 @@ int r433b_process(r433b_ctx *ctx, r433b_batch const *b)
             raw = ctx->d_raw.p;
         }
         size_t n4 = (size_t)(2 * total_bytes / 16); // groups of four floats (offsets are multiples of 32 bytes)
-        k_cf32_to_cs16<<<ctx->n_sms * 8, 256, 0, st>>>((float4 const *)raw, (uint2 *)ctx->d_data.p, n4);
+        R4_LAUNCH(k_cf32_to_cs16, ctx->n_sms * 8, 256, 0, st, (float4 const *)raw, (uint2 *)ctx->d_data.p, n4);
         CU(cudaGetLastError());
     } else if (!b->data_on_device && total_bytes)
         CU(cudaMemcpyAsync(ctx->d_data.p, b->data, total_bytes, cudaMemcpyHostToDevice, st));
@@ -621,7 +622,7 @@ int r433b_process(r433b_ctx *ctx, r433b_batch const *b)
             all.pkg_end = ctx->n_pkgs;
             CU(cudaMemcpyAsync(ctx->d_ranges.p, &all, sizeof(all), cudaMemcpyHostToDevice, st));
             q.range = (GroupRange *)ctx->d_ranges.p;
-            k_slice<<<slice_grid, kSliceThreads, 0, st>>>(q);
+            R4_LAUNCH(k_slice, slice_grid, kSliceThreads, 0, st, q);
             CU(cudaGetLastError());
             slice_launches++;
             CU(cudaMemcpyAsync(cursor, ctx->d_cursor.p, sizeof(cursor), cudaMemcpyDeviceToHost, st));

@@ -13,8 +13,10 @@
 
 #ifdef __CUDACC__
 #define R4_HD __host__ __device__ __forceinline__
+#define R4_HD_COLD __host__ __device__ __noinline__
 #else
 #define R4_HD inline
+#define R4_HD_COLD inline
 #endif
 
 namespace r433b {
@@ -221,19 +223,25 @@ R4_HD void put(int *arr, unsigned &hw, unsigned i, int v)
     if (i + 1 > hw) hw = i + 1;
 }
 
-// src/pulse_data.c:27-34 on the FSK train (offset grows by the COUNT: kept quirk)
+// src/pulse_data.c:27-34 on the FSK train (offset grows by the COUNT: kept quirk).  The memory move is out
+// of line (cold, and the sub-detectors that call it are inlined several times); no state escapes into it.
 template <class Ctx>
-R4_HD void fsk_shift(DetState &d, Trains const &t, Ctx &cx)
+R4_HD_COLD void fsk_shift_move(int *pulse, int *gap, Ctx cx)
 {
     int const half = kMaxPulses / 2;
     cx.sync();
     for (int i = cx.lane; i < half; i += cx.nlanes) {
-        t.fsk_pulse[i] = t.fsk_pulse[i + half];
-        t.fsk_gap[i] = t.fsk_gap[i + half];
+        pulse[i] = pulse[i + half];
+        gap[i] = gap[i + half];
     }
     cx.sync();
-    d.fsk_n -= half;
-    d.fsk_offset += half;
+}
+template <class Ctx>
+R4_HD void fsk_shift(DetState &d, Trains const &t, Ctx &cx)
+{
+    fsk_shift_move(t.fsk_pulse, t.fsk_gap, cx);
+    d.fsk_n -= kMaxPulses / 2;
+    d.fsk_offset += kMaxPulses / 2;
     d.fsk_hw = kMaxPulses;
 }
 
@@ -416,14 +424,27 @@ R4_HD void close_fsk(DetState &d, Trains const &t, int fpdm)
 // Returns 0: sample consumed; 1: OOK package complete; 2: FSK package complete.
 // On 1/2 the sample has NOT been consumed: the caller emits, applies det_call_boundary()
 // and presents the same sample again (the reference returns before `data_counter += 1`).
-template <class Ctx>
+//
+// `defer_f1`: the carrier estimate of an OOK package (pulses->fsk_f1_est, :365) is only READ when the
+// package is returned.  With defer_f1 the update is not applied after the first pulse; the return value
+// carries kStepF1Deferred instead and the caller logs the sample (k_detect evaluates the estimate when the
+// package ends, from the logged samples: r433b_detect.cuh).  `f` is then only looked at while
+// ook_n == 0 (the FSK sub-detector and the estimate of the first pulse).
+//
+// Mode kStepLean compiles the FSK sub-detector out: valid whenever ook_n != 0 or the state is IDLE / GAP.
+// Mode kStepFirst only has the PULSE / GAP_START branches: valid inside a first pulse (ook_n == 0).  k_detect
+// keeps the lean instance on its hot path and enters the other only inside first pulses; kStepAll is everything.
+enum { kStepF1Deferred = 4 };
+enum { kStepAll = 0, kStepLean = 1, kStepFirst = 2 };
+template <int Mode = kStepAll, class Ctx>
 R4_HD int det_step(DetState &d, Levels const &lv, Trains const &t, int a, int f, unsigned long long pos,
-        int per_ms, int fpdm, Ctx &cx)
+        int per_ms, int fpdm, Ctx &cx, bool defer_f1 = false)
 {
+    constexpr bool WithFsk = Mode != kStepLean;
     Thresholds th = det_thresholds(d.low, d.high, lv);
     bool const above = a > th.up;
     bool const below = a < th.down;
-    if (d.st == kIdle) {
+    if (Mode != kStepFirst && d.st == kIdle) {
         if (above && d.lead_in > kLeadIn)
             begin_package(d, t, pos, cx);
         else
@@ -431,6 +452,7 @@ R4_HD int det_step(DetState &d, Levels const &lv, Trains const &t, int a, int f,
         return 0;
     }
     d.run += 1;
+    int deferred = 0;
     if (d.st == kPulse) {
         if (below) {
             if (d.run < kMinPulseSamples) {
@@ -450,15 +472,18 @@ R4_HD int det_step(DetState &d, Levels const &lv, Trains const &t, int a, int f,
         } else {
             d.high += a / 64 - d.high / 64;
             if (d.high < lv.min_high) d.high = lv.min_high;
-            d.ook_f1 += f / 64 - d.ook_f1 / 64;
+            if (defer_f1 && d.ook_n != 0)
+                deferred = kStepF1Deferred;
+            else
+                d.ook_f1 += f / 64 - d.ook_f1 / 64;
         }
-        if (d.ook_n == 0) {
+        if (WithFsk && d.ook_n == 0) {
             if (fpdm == 0)
                 fsk_classic(d, t, f, cx);
             else
                 fsk_minmax(d, t, f, cx);
         }
-        return 0;
+        return deferred;
     }
     if (d.st == kGapStart) {
         if (above) {
@@ -466,12 +491,12 @@ R4_HD int det_step(DetState &d, Levels const &lv, Trains const &t, int a, int f,
             d.st = kPulse;
         } else if (d.run >= kMinPulseSamples) {
             d.st = kGap;
-            if (d.fsk_n > (unsigned)kMinPulses) {
+            if (WithFsk && d.fsk_n > (unsigned)kMinPulses) { // only the first pulse feeds the FSK train: later gaps find fsk_n <= 16 (else the package ended here)
                 close_fsk(d, t, fpdm);
                 return 2;
             }
         }
-        if (d.ook_n == 0) {
+        if (WithFsk && d.ook_n == 0) {
             if (fpdm == 0)
                 fsk_classic(d, t, f, cx);
             else
@@ -480,6 +505,7 @@ R4_HD int det_step(DetState &d, Levels const &lv, Trains const &t, int a, int f,
         return 0;
     }
     // kGap
+    if (Mode == kStepFirst) return 0; // not reached: a first-pulse step is PULSE or GAP_START
     if (above) {
         put(t.ook_gap, d.ook_hw, d.ook_n, d.run);
         d.ook_n += 1;

@@ -1,0 +1,1292 @@
+// r433b_detect.cuh -- k_detect: IQ -> packages, one WARP per capture stream (sm_100a).
+//
+// The warp walks its stream in tiles of 2048 samples.  Per tile:
+//
+//  1. AM front, lane-parallel and exact.  Lane l owns the 64 consecutive samples [64 l, 64 l + 64) of the
+//     tile (one 128-byte line of cu8 IQ).  The envelope low-pass y' = (a y + b (x + x')) >> 14
+//     (src/baseband.c:145-169) is a floor map, not associative -- but it contracts by a / 2^14 = 0.854 per
+//     sample, so a trajectory started from ANY state is, after a few dozen samples of live signal, the true
+//     one.  Every lane therefore starts kWarmAm samples in front of its chunk from a guess (the local
+//     envelope), runs ONE trajectory through warm-up and chunk, and the warp then VERIFIES: lane l's state
+//     at its chunk boundary must equal lane l-1's state at its chunk end.  Lane 0 starts from the carried
+//     exact state, so by induction a clean check proves every lane exact.  A lane that fails (about one
+//     chunk in a thousand) redoes its chunk from the now-known exact start.  No monotonicity is needed,
+//     constant input only makes the redo chain longer.  One envelope needs 2.5 instructions (xor + 2 and +
+//     2 dp4a per pair of samples), one filter step 4; AM goes to shared memory as 16 bits per sample.
+//
+//  2. The package detector (src/pulse_detect.c:199-483) walks the tile warp-uniformly with ballot scans for
+//     the states whose thresholds are frozen (IDLE stretches by bracket rounds, GAP, GAP_START) and a
+//     sequential but lean recurrence for the high-level estimator of PULSE.
+//
+//  3. FM (src/baseband.c:181-366) is only READ in two places: by the FSK sub-detector during the first
+//     pulse of a package, and by the carrier estimate `fsk_f1_est`, which is reported when a package ends.
+//     Neither needs FM for every sample:
+//       * FM WINDOWS of 256 samples are made on demand (discriminator lane-parallel from the IQ bytes,
+//         low-pass by sub-chunks with the same start-from-a-guess / verify / redo scheme).  The filter state
+//         in front of a window that does not continue the previous one is rebuilt RIGOROUSLY: both ends of
+//         the whole state range are pushed through the samples in front of the window until they meet
+//         (monotone filter: the host proves a1, b0 >= 0, a1 + 2 b0 <= unity; otherwise FM is made for
+//         every window of every tile).
+//       * the carrier estimate g' = g + f/64 - g/64 is DEFERRED after the first pulse: the walk only logs
+//         which samples update it.  When the package ends, g is evaluated over the newest ~1500 logged
+//         samples from both ends of its range; the recurrence forgets its start at 63/64 per sample, the two
+//         ends meet, and a met pair is the exact value.  If they do not meet (exactly constant input), the
+//         evaluation goes further back, in the end over the whole log from the exactly known value after
+//         the first pulse.  A full log is folded into that value the same way.
+//
+// IQ is read once from HBM (plus L1/L2 hits for the warm-up overlap and the FM windows); no intermediate
+// ever leaves the SM.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/r433b.h"
+#include "r433b_core.cuh"
+
+#ifdef R433B_SIMT_EMU
+#define R4_DYN_SMEM(type, name) type *name = reinterpret_cast<type *>(simt::st().dyn_smem)
+#define R4_NOINLINE
+#else
+#define R4_DYN_SMEM(type, name) extern __shared__ __align__(16) type name[]
+#define R4_NOINLINE __noinline__
+#endif
+
+#ifndef R4_NO_PULSE0
+#define R4_NO_PULSE0 0
+#endif
+namespace r433b {
+
+constexpr int kTrainInts = 4 * kMaxPulses; // per-stream scratch: ook pulse/gap, fsk pulse/gap
+constexpr int kDetectWarps = 4;            // warps (streams) per CTA
+constexpr int kDetectCtasPerSm = 7;        // 28 warps per SM: 4096 streams are co-resident on 148 SMs
+
+constexpr int kChunk = 64;                 // samples per lane per tile
+constexpr int kTile = 32 * kChunk;         // 2048
+constexpr int kAmStride = kChunk / 2 + 1;  // words between lane chunks of the 16-bit AM tile (odd: conflict-free)
+constexpr int kAmWords = 32 * kAmStride;
+constexpr int kWarmAm = 64;                // warm-up samples of the AM trajectory (multiple of 16, <= kChunk)
+constexpr int kFmWin = 256;                // FM window
+constexpr int kFmSub = kFmWin / 32;        // samples per lane of a window
+constexpr int kFmPadded = kFmWin + kFmWin / kFmSub; // padded index space: i + i / kFmSub
+constexpr int kWarmFm = 48;                // warm-up samples of the FM trajectories
+constexpr int kFmWindowsPerTile = kTile / kFmWin;
+constexpr unsigned kLogCap = 1024;         // deferred carrier-estimate log: entries per stream
+constexpr int kF1Tail = 1536;              // samples of the first evaluation attempt
+
+// Shared memory of one warp
+struct alignas(16) WarpSmem {
+    uint32_t am[kAmWords];       // AM tile, 16 bits per sample: sample n at u16 (n / 64) * 66 + n % 64
+    uint32_t xf[kFmPadded];      // discriminator outputs of the current FM window (padded index)
+    uint16_t fm[kFmPadded];      // FM (or the raw-envelope alias) of the current window
+    int q[32];                   // chain operands of one 32-sample step
+    int cmin[32], cmax[32];      // per lane chunk: bounds of its AM values
+    // FM bookkeeping (warp-uniform; written by lane 0)
+    unsigned long long fm_pos;   // (fm_y, fm_xf) is the exact filter state after sample fm_pos - 1
+    int fm_y, fm_xf;
+    unsigned long long win0;     // the window holds FM of [win0, win0 + win_n)
+    int win_n;
+    int tile_state_y[kFmWindowsPerTile], tile_state_xf[kFmWindowsPerTile]; // eager mode: state in front of each window
+    unsigned long long tile_end_pos; // eager mode: the contiguous filter state at the end of the tile pass
+    int tile_end_y, tile_end_xf;
+    DetState park;
+};
+
+// Everything one stream carries from one launch to the next when a batch is processed in time slices.
+struct StreamState {
+    DetState d;
+    int y_am, x_prev;
+    unsigned long long fm_pos;
+    int fm_y, fm_xf;
+    unsigned log_n, last_start, last_count;
+    unsigned seq;
+    int flushed;
+};
+
+struct DetectParams {
+    uint8_t const *data;
+    unsigned long long const *offsets; // bytes, n_streams + 1
+    unsigned long long const *lengths; // optional: bytes of stream i actually used
+    unsigned n_streams;
+    unsigned stream0, stream_end;      // the streams this launch covers
+    unsigned long long sample_begin, sample_end; // the slice of every stream this launch covers (multiples of the tile)
+    int first_chunk;                   // start from reset_sdr_flow() state instead of the saved one
+    struct StreamState *state;         // per-stream carried state between launches of one batch
+    int use_mag, enable_fm, fpdm;
+    int lazy_fm;   // make FM windows on demand (needs the monotone FM filter: wrap_free)
+    unsigned flip; // XOR mask applied to every loaded word: 0x80808080 turns cs8 into cu8
+    unsigned rate, block_samples;
+    Levels lv;
+    int lpf_a1, lpf_b0, fm_a1, fm_b0;
+    int wrap_free;
+    int *train_scratch;
+    unsigned *log_scratch;             // n_streams * kLogCap * 2
+    r433b_package *pkgs;
+    unsigned pkg_cap;
+    int *pulse_pool, *gap_pool;
+    unsigned pool_cap;
+    unsigned *counters; // [0] packages, [1] pool entries, [2] overflow flag, [4..] statistics
+    int16_t *am_out, *fm_out; // optional stage dump, indexed by offsets[s]/SS + n
+};
+
+struct WarpCtx {
+    int lane;
+    int nlanes;
+    __device__ __forceinline__ void sync() { __syncwarp(); }
+};
+
+template <int SS>
+struct Fmt {
+    static constexpr int SPL = 16 / SS; // samples per 128-bit load
+};
+
+// 16 contiguous bytes (8 cu8 / 4 cs16 samples) starting at sample `pos` of the stream: one 128-bit load;
+// zero-filled past `n_valid` samples counted from pos.
+template <int SS>
+__device__ __forceinline__ void load_group(uint8_t const *src, unsigned long long pos, long long n_valid, unsigned flip,
+        uint32_t (&rw)[4])
+{
+    constexpr int SPL = 16 / SS;
+    uint8_t const *g = src + pos * SS;
+    if (n_valid >= SPL) {
+        uint4 v = __ldg(reinterpret_cast<uint4 const *>(g));
+        rw[0] = v.x ^ flip;
+        rw[1] = v.y ^ flip;
+        rw[2] = v.z ^ flip;
+        rw[3] = v.w ^ flip;
+    } else {
+        rw[0] = rw[1] = rw[2] = rw[3] = 0u;
+        int nb = n_valid > 0 ? (int)n_valid * SS : 0;
+        for (int bidx = 0; bidx < nb; ++bidx) rw[bidx >> 2] |= (uint32_t)(g[bidx] ^ (flip & 0xff)) << (8 * (bidx & 3));
+    }
+}
+
+// -Y magest on cu8 (src/baseband.c:65-79): rarely asked for, kept out of the hot loops' instruction stream
+// (two magnitudes per returned word: they are below 2^15)
+__device__ R4_NOINLINE uint4 mag_group_cu8(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3)
+{
+    auto two = [](uint32_t w) {
+        return (uint32_t)mag_cu8((int)(w & 0xff), (int)((w >> 8) & 0xff))
+                | ((uint32_t)mag_cu8((int)((w >> 16) & 0xff), (int)(w >> 24)) << 16);
+    };
+    uint4 r;
+    r.x = two(w0);
+    r.y = two(w1);
+    r.z = two(w2);
+    r.w = two(w3);
+    return r;
+}
+
+// envelope / magnitude of the SPL samples of one group (src/baseband.c:36-45, :65-79, :96-110)
+template <int SS>
+__device__ __forceinline__ void env_group(uint32_t const (&rw)[4], int use_mag, int (&x)[16 / SS])
+{
+    if (SS == 2) {
+        if (!use_mag) {
+            // (127 - I)^2 + (127 - Q)^2: 127 - v is v ^ 0x7f read as a signed byte; one dp4a squares and adds a pair
+#pragma unroll
+            for (int w = 0; w < 4; ++w) {
+                uint32_t s = rw[w] ^ 0x7f7f7f7fu;
+                x[2 * w] = __dp4a((int)s, (int)(s & 0x0000ffffu), 0);
+                x[2 * w + 1] = __dp4a((int)s, (int)(s & 0xffff0000u), 0);
+            }
+        } else {
+            uint4 const m = mag_group_cu8(rw[0], rw[1], rw[2], rw[3]);
+            x[0] = (int)(m.x & 0xffff);
+            x[1] = (int)(m.x >> 16);
+            x[2] = (int)(m.y & 0xffff);
+            x[3] = (int)(m.y >> 16);
+            x[4] = (int)(m.z & 0xffff);
+            x[5] = (int)(m.z >> 16);
+            x[6] = (int)(m.w & 0xffff);
+            x[7] = (int)(m.w >> 16);
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 16 / SS; ++j) {
+            uint32_t w = rw[j & 3];
+            x[j] = mag_cs16((int)(int16_t)(w & 0xffff), (int)(int16_t)(w >> 16));
+        }
+    }
+}
+
+__device__ __forceinline__ int fm_pidx(int i) { return i + i / kFmSub; }
+
+// ------------------------------------------------------------------------------ FM --------
+
+// IQ of one sample (centred) out of a loaded group
+template <int SS>
+__device__ __forceinline__ void iq_of(uint32_t const (&rw)[4], int j, int &ci, int &cq)
+{
+    if (SS == 2) {
+        uint32_t w = rw[j >> 1] >> ((j & 1) * 16);
+        ci = (int)(w & 0xff) - 128;
+        cq = (int)((w >> 8) & 0xff) - 128;
+    } else {
+        uint32_t w = rw[j & 3];
+        ci = (int)(int16_t)(w & 0xffff);
+        cq = (int)(int16_t)(w >> 16);
+    }
+}
+
+// one low-pass step of the FM filter (src/baseband.c:263 / :357); the cu8 state is an int16 store
+template <int SS>
+__device__ __forceinline__ int fm_step(int y, long long a1, long long b0, int v, int vp)
+{
+    if (SS == 2) return iir16(y, (int)a1, (int)b0, v + vp);
+    return iir32(y, a1, b0, (long long)v + vp);
+}
+
+template <int SS>
+struct FmJob {
+    uint8_t const *src;        // the stream
+    unsigned long long N;      // its length in samples
+    unsigned flip;
+    long long a1, b0;
+    int fm_on;                 // 0: "FM" is the raw envelope (buf.fm aliases buf.temp when nothing asks for FM)
+    int use_mag;
+    int monotone;              // the state rebuild by range collapse is valid
+    int16_t *fm_out;           // stage dump (absolute index = stream base + sample) or nullptr
+};
+
+// Discriminator outputs (src/baseband.c:253-262 / :346-356) of samples [a, a + n) into sm.xf[fm_pidx(i)],
+// n <= kFmWin, a a multiple of SPL; lane j of a batch takes the group at a + 32 * SPL * q + SPL * j.
+// With !fm_on the raw envelope goes straight to sm.fm instead.
+template <int SS>
+__device__ void disc_fill(FmJob<SS> const &jb, WarpSmem &sm, unsigned long long a, int n)
+{
+    constexpr int SPL = 16 / SS;
+    int const lane = threadIdx.x & 31;
+    int pri = 0, prq = 0; // IQ in front of the batch (zero in front of the stream: reset demod state)
+    if (jb.fm_on && a > 0) {
+        uint8_t const *g = jb.src + (a - 1) * SS;
+        if (SS == 2) {
+            pri = (int)(g[0] ^ (jb.flip & 0xff)) - 128;
+            prq = (int)(g[1] ^ (jb.flip & 0xff)) - 128;
+        } else {
+            uint32_t w = *reinterpret_cast<uint32_t const *>(g) ^ jb.flip;
+            pri = (int)(int16_t)(w & 0xffff);
+            prq = (int)(int16_t)(w >> 16);
+        }
+    }
+#pragma unroll 1
+    for (int base = 0; base < n; base += 32 * SPL) {
+        int const i0 = base + lane * SPL;
+        uint32_t rw[4];
+        load_group<SS>(jb.src, a + (unsigned long long)i0, i0 < n ? (long long)(jb.N - a) - i0 : 0, jb.flip, rw);
+        if (!jb.fm_on) {
+            int x[SPL];
+            env_group<SS>(rw, jb.use_mag, x);
+#pragma unroll
+            for (int j = 0; j < SPL; ++j)
+                if (i0 + j < n) sm.fm[fm_pidx(i0 + j)] = (uint16_t)x[j];
+            continue;
+        }
+        int li, lq;
+        iq_of<SS>(rw, SPL - 1, li, lq);
+        int pi_ = __shfl_up_sync(0xffffffffu, li, 1);
+        int pq_ = __shfl_up_sync(0xffffffffu, lq, 1);
+        if (lane == 0) {
+            pi_ = pri;
+            pq_ = prq;
+        }
+        pri = __shfl_sync(0xffffffffu, li, 31);
+        prq = __shfl_sync(0xffffffffu, lq, 31);
+#pragma unroll
+        for (int j = 0; j < SPL; ++j) {
+            int ci, cq, xf;
+            iq_of<SS>(rw, j, ci, cq);
+            if (SS == 2) {
+                xf = atan16(cq * pi_ - ci * pq_, ci * pi_ + cq * pq_);
+            } else {
+                long long re = (long long)ci * pi_ + (long long)cq * pq_;
+                long long im = (long long)cq * pi_ - (long long)ci * pq_;
+                xf = atan32((int)(unsigned)(unsigned long long)im, (int)(unsigned)(unsigned long long)re);
+            }
+            pi_ = ci;
+            pq_ = cq;
+            if (i0 + j < n) sm.xf[fm_pidx(i0 + j)] = (uint32_t)xf;
+        }
+    }
+    __syncwarp();
+}
+
+// The exact FM filter state in front of sample `pos` (after sample pos - 1), without knowing anything
+// before: both ends of the state range go through the K samples in front of pos; when they meet, the value
+// is independent of everything earlier.  K grows until they meet or the walk starts at a known state
+// (the stream start, or sm.fm_pos).  Monotone filters only.  Leaves the state in sm.fm_pos / fm_y / fm_xf.
+template <int SS>
+__device__ R4_NOINLINE void fm_cold(FmJob<SS> const &jb, WarpSmem &sm, unsigned long long pos)
+{
+    constexpr int SPL = 16 / SS;
+    int const lane = threadIdx.x & 31;
+    unsigned long long const known = sm.fm_pos; // state known here (always <= pos when used)
+    for (unsigned long long K = 64;; K *= 4) {
+        unsigned long long a = pos > K ? (pos - K) / SPL * SPL : 0;
+        bool exact_start = a == 0;
+        int lo, hi, fp;
+        if (known <= pos && known >= a) { // reach back to the known state instead
+            a = known;
+            exact_start = true;
+        }
+        if (exact_start) {
+            lo = hi = a == known ? sm.fm_y : 0;
+            fp = a == known ? sm.fm_xf : 0;
+        } else {
+            lo = SS == 2 ? -32768 : (int)0x80000000;
+            hi = SS == 2 ? 32767 : 0x7fffffff;
+            fp = 0; // replaced below by the sample in front of the first processed one
+        }
+        // pieces of kFmWin samples, sequential chain carried across them
+        bool first_piece = true;
+        for (unsigned long long p0 = a; p0 < pos; p0 += kFmWin) {
+            int const n = pos - p0 < (unsigned long long)kFmWin ? (int)(pos - p0) : kFmWin;
+            disc_fill<SS>(jb, sm, p0, n);
+            int k = 0;
+            if (first_piece && !exact_start) { // the first sample only provides x[n-1]
+                fp = (int)sm.xf[fm_pidx(0)];
+                k = 1;
+            }
+            first_piece = false;
+#pragma unroll 2
+            for (; k < n; ++k) {
+                int v = (int)sm.xf[fm_pidx(k)];
+                lo = fm_step<SS>(lo, jb.a1, jb.b0, v, fp);
+                hi = fm_step<SS>(hi, jb.a1, jb.b0, v, fp);
+                fp = v;
+            }
+            __syncwarp();
+        }
+        if (lo == hi) {
+            if (lane == 0) {
+                sm.fm_pos = pos;
+                sm.fm_y = lo;
+                sm.fm_xf = fp;
+                sm.win_n = 0;
+            }
+            __syncwarp();
+            return;
+        }
+        // not met: exactly constant input parks the two ends on different fixed points of the floor map
+    }
+}
+
+// FM of the window [w0, w0 + n) (n <= kFmWin, w0 a multiple of SPL) from the exact state in sm.fm_* which
+// must be the one in front of w0.  Advances sm.fm_pos to w0 + n.
+template <int SS>
+__device__ R4_NOINLINE void fm_window(FmJob<SS> const &jb, WarpSmem &sm, unsigned long long w0, int n)
+{
+    int const lane = threadIdx.x & 31;
+    disc_fill<SS>(jb, sm, w0, n);
+    if (jb.fm_on) {
+        int const base = lane * kFmSub;
+        int nv = n - base;
+        nv = nv < 0 ? 0 : (nv > kFmSub ? kFmSub : nv);
+        int start = base - kWarmFm;
+        bool const exact = start <= 0;
+        int y, fp;
+        if (exact) {
+            start = 0;
+            y = sm.fm_y;
+            fp = sm.fm_xf;
+        } else {
+            fp = (int)sm.xf[fm_pidx(start - 1)];
+            y = SS == 2 ? fp : fp; // the low-pass has unit gain: its state is near its input
+        }
+        if (nv > 0) {
+#pragma unroll 4
+            for (int k = start; k < base; ++k) {
+                int v = (int)sm.xf[fm_pidx(k)];
+                y = fm_step<SS>(y, jb.a1, jb.b0, v, fp);
+                fp = v;
+            }
+        }
+        int const y_b = y, fp_b = fp;
+        int y_end = y;
+        // verify / redo loop: the state a lane reached at its chunk boundary must be what its left neighbour
+        // ended with; the lowest lane that fails runs again from that (exact) state
+        int ys = y_b;
+        bool run = true, fixed = false;
+        for (;;) {
+            if (run) {
+                int yy = ys, ff = fp_b;
+                for (int k = 0; k < nv; ++k) {
+                    int v = (int)sm.xf[fm_pidx(base + k)];
+                    yy = fm_step<SS>(yy, jb.a1, jb.b0, v, ff);
+                    ff = v;
+                    sm.fm[fm_pidx(base + k)] = (uint16_t)(int16_t)(SS == 2 ? yy : (yy >> 16));
+                }
+                y_end = yy;
+                fp = ff;
+            }
+            int prev_end = __shfl_up_sync(0xffffffffu, y_end, 1);
+            bool ok = exact || fixed || nv == 0 || y_b == prev_end;
+            unsigned bad = __ballot_sync(0xffffffffu, !ok);
+            if (!bad) break;
+            int const f = __ffs(bad) - 1; // lanes below f are exact
+            ys = __shfl_sync(0xffffffffu, y_end, f - 1);
+            run = lane == f;
+            if (run) fixed = true;
+        }
+        int const last = (n - 1) / kFmSub;
+        int ye = __shfl_sync(0xffffffffu, y_end, last);
+        int fe = __shfl_sync(0xffffffffu, fp, last);
+        if (lane == 0) {
+            sm.fm_y = ye;
+            sm.fm_xf = fe;
+        }
+    }
+    if (lane == 0) {
+        sm.fm_pos = w0 + n;
+        sm.win0 = w0;
+        sm.win_n = n;
+    }
+    __syncwarp();
+    if (jb.fm_out) { // stage dump
+        for (int i = lane; i < n; i += 32) jb.fm_out[w0 + i] = (int16_t)sm.fm[fm_pidx(i)];
+    }
+}
+
+// Make the window that holds sample `pos` current (lazy mode): continue the previous window when it ends
+// close in front, rebuild the state otherwise.
+template <int SS>
+__device__ R4_NOINLINE void fm_demand(FmJob<SS> const &jb, WarpSmem &sm, unsigned long long pos, unsigned long long limit)
+{
+    constexpr int SPL = 16 / SS;
+    unsigned long long w0 = pos / SPL * SPL;
+    if (jb.fm_on) {
+        unsigned long long const have = sm.fm_pos;
+        if (have > w0 || w0 - have > 2 * kFmWin) {
+            fm_cold<SS>(jb, sm, w0);
+        } else {
+            while (sm.fm_pos + kFmWin <= w0) fm_window<SS>(jb, sm, sm.fm_pos, kFmWin); // walk up to it
+            w0 = sm.fm_pos;
+        }
+    }
+    unsigned long long end = w0 + kFmWin < limit ? w0 + kFmWin : limit;
+    fm_window<SS>(jb, sm, w0, (int)(end - w0));
+}
+
+// The window for the detector walk at tile [t0, t0 + nv_tile): on demand (lazy), or re-made from the start
+// states the tile pass kept (eager mode: windows are aligned, the end-of-tile state is put back afterwards).
+template <int SS>
+__device__ R4_NOINLINE void fm_for_walk(FmJob<SS> const &jb, WarpSmem &sm, unsigned long long pos, unsigned long long t0,
+        int nv_tile, bool lazy)
+{
+    int const lane = threadIdx.x & 31;
+    if (lazy) {
+        fm_demand<SS>(jb, sm, pos, t0 + (unsigned long long)nv_tile);
+        return;
+    }
+    int const w = (int)(pos - t0) / kFmWin;
+    if (lane == 0) {
+        sm.fm_y = sm.tile_state_y[w];
+        sm.fm_xf = sm.tile_state_xf[w];
+        sm.fm_pos = t0 + (unsigned long long)w * kFmWin;
+    }
+    __syncwarp();
+    FmJob<SS> quiet = jb;
+    quiet.fm_out = nullptr;
+    int const cnt = nv_tile - w * kFmWin < kFmWin ? nv_tile - w * kFmWin : kFmWin;
+    fm_window<SS>(quiet, sm, t0 + (unsigned long long)w * kFmWin, cnt);
+    if (lane == 0) {
+        sm.fm_pos = sm.tile_end_pos;
+        sm.fm_y = sm.tile_end_y;
+        sm.fm_xf = sm.tile_end_xf;
+    }
+    __syncwarp();
+}
+
+// ---------------------------------------------------- deferred carrier estimate ---------
+
+// src/pulse_detect.c:365 on one sample
+__device__ __forceinline__ int f1_step(int g, int f) { return g + f / 64 - g / 64; }
+
+// Evaluate the deferred updates of the carrier estimate: d.ook_f1 holds the exact value in front of the
+// first logged sample; the log (entries = runs of consecutive updating samples, relative to the package
+// start) is in global memory except for the newest entry.  Returns the exact estimate after the last one.
+template <int SS>
+__device__ R4_NOINLINE int f1_evaluate(FmJob<SS> const &jb, WarpSmem &sm, unsigned const *log, unsigned long long start_abs,
+        int g_base, unsigned n_closed, unsigned open_start, unsigned open_count)
+{
+    int const lane = threadIdx.x & 31;
+    // n_closed entries are in global memory, the open one (if any) comes in the arguments
+    unsigned const total_entries = n_closed + (open_count ? 1u : 0u);
+    if (!total_entries) return g_base;
+    auto entry = [&](unsigned i, unsigned &st, unsigned &cnt) {
+        if (i < n_closed) {
+            st = log[2 * i];
+            cnt = log[2 * i + 1];
+        } else {
+            st = open_start;
+            cnt = open_count;
+        }
+    };
+    for (unsigned long long want = kF1Tail;; want *= 4) {
+        // the shortest suffix of the log with at least `want` samples
+        unsigned j0 = total_entries;
+        unsigned long long have = 0;
+        while (j0 > 0 && have < want) {
+            unsigned st, cnt;
+            entry(j0 - 1, st, cnt);
+            have += cnt;
+            --j0;
+        }
+        int lo, hi;
+        if (j0 == 0) {
+            lo = hi = g_base;
+        } else { // |g| <= 64 * 512 + 63 always
+            lo = -40000;
+            hi = 40000;
+        }
+        for (unsigned j = j0; j < total_entries; ++j) {
+            unsigned st, cnt;
+            entry(j, st, cnt);
+            unsigned long long pos = start_abs + st;
+            while (cnt) {
+                if (!(sm.win_n > 0 && pos >= sm.win0 && pos < sm.win0 + (unsigned long long)sm.win_n))
+                    fm_demand<SS>(jb, sm, pos, jb.N);
+                unsigned long long wend = sm.win0 + (unsigned long long)sm.win_n;
+                unsigned take = wend - pos < cnt ? (unsigned)(wend - pos) : cnt;
+                int const i0 = (int)(pos - sm.win0);
+                // operands f / 64 of up to 32 samples at a time, lane-parallel into shared memory; the chain then
+                // reads four per load
+                for (unsigned done = 0; done < take; done += 32) {
+                    int const m = take - done < 32 ? (int)(take - done) : 32;
+                    __syncwarp();
+                    if (lane < m) sm.q[lane] = (int)(int16_t)sm.fm[fm_pidx(i0 + (int)done + lane)] / 64;
+                    __syncwarp();
+                    int k = 0;
+                    if (lo == hi) {
+                        for (; k + 4 <= m; k += 4) {
+                            int4 const b = *reinterpret_cast<int4 const *>(&sm.q[k]);
+                            lo += b.x - lo / 64;
+                            lo += b.y - lo / 64;
+                            lo += b.z - lo / 64;
+                            lo += b.w - lo / 64;
+                        }
+                        for (; k < m; ++k) lo += sm.q[k] - lo / 64;
+                        hi = lo;
+                    } else {
+                        for (; k < m; ++k) {
+                            int const q = sm.q[k];
+                            lo += q - lo / 64;
+                            hi += q - hi / 64;
+                        }
+                    }
+                }
+                pos += take;
+                cnt -= take;
+            }
+        }
+        if (lo == hi) return lo;
+        // j0 == 0 started from one exact value, so lo == hi there: the loop always ends
+    }
+}
+
+// --------------------------------------------------------------------------- kernel ------
+
+template <int SS>
+__global__ void __launch_bounds__(kDetectWarps * 32, kDetectCtasPerSm) k_detect(DetectParams p)
+{
+    constexpr int SPL = 16 / SS;
+    constexpr int C = kChunk;
+    constexpr int T = kTile;
+    R4_DYN_SMEM(uint32_t, smem_raw);
+
+    int const warp = threadIdx.x >> 5;
+    int const lane = threadIdx.x & 31;
+    unsigned const s = p.stream0 + blockIdx.x * kDetectWarps + warp;
+    if (s >= p.stream_end) return;
+
+    WarpSmem &sm = reinterpret_cast<WarpSmem *>(smem_raw)[warp];
+    uint16_t const *am16 = reinterpret_cast<uint16_t const *>(sm.am);
+    bool const fm_on = p.enable_fm != 0;
+
+    unsigned long long const byte0 = p.offsets[s];
+    unsigned long long const N = (p.lengths ? p.lengths[s] : p.offsets[s + 1] - byte0) / SS;
+    uint8_t const *const src = p.data + byte0;
+
+    Trains tr;
+    tr.ook_pulse = p.train_scratch + (size_t)s * kTrainInts;
+    tr.ook_gap = tr.ook_pulse + kMaxPulses;
+    tr.fsk_pulse = tr.ook_gap + kMaxPulses;
+    tr.fsk_gap = tr.fsk_pulse + kMaxPulses;
+    unsigned *const log = p.log_scratch + (size_t)s * kLogCap * 2;
+
+    WarpCtx cx;
+    cx.lane = lane;
+    cx.nlanes = 32;
+
+    FmJob<SS> jb;
+    jb.src = src;
+    jb.N = N;
+    jb.flip = p.flip;
+    jb.a1 = p.fm_a1;
+    jb.b0 = p.fm_b0;
+    jb.fm_on = p.enable_fm;
+    jb.use_mag = p.use_mag;
+    jb.monotone = p.wrap_free;
+    jb.fm_out = p.fm_out ? p.fm_out + byte0 / SS : nullptr;
+    // FM windows on demand need the rigorous state rebuild (monotone filter); the stage dump wants every sample
+    bool const lazy_fm = !fm_on || (p.wrap_free && p.lazy_fm && !p.am_out);
+    // the deferred carrier estimate re-makes FM for logged samples later: needs the state rebuild as well
+    bool const defer_f1 = !fm_on || p.wrap_free != 0;
+
+    DetState d;
+    unsigned seq = 0;
+    int const per_ms = (int)(p.rate / 1000);
+    int y_am = 0, x_prev = 0; // carried AM filter state (reset_sdr_flow(): zero)
+    int flushed = 0;
+    unsigned log_n = 0, log_start = 0, log_count = 0; // deferred carrier-estimate log: closed entries, the open entry
+    if (p.first_chunk) {
+        det_reset(d);
+        d.ook_hw = d.fsk_hw = kMaxPulses; // scratch is not assumed to be zero: first package clears it
+        if (lane == 0) {
+            sm.fm_pos = 0;
+            sm.fm_y = sm.fm_xf = 0;
+        }
+    } else {
+        StreamState const &ss = p.state[s];
+        d = ss.d;
+        y_am = ss.y_am;
+        x_prev = ss.x_prev;
+        seq = ss.seq;
+        flushed = ss.flushed;
+        if (lane == 0) {
+            sm.fm_pos = ss.fm_pos;
+            sm.fm_y = ss.fm_y;
+            sm.fm_xf = ss.fm_xf;
+        }
+        log_n = ss.log_n;
+        log_start = ss.last_start;
+        log_count = ss.last_count;
+    }
+    if (lane == 0) {
+        sm.win0 = 0;
+        sm.win_n = 0;
+    }
+    __syncwarp();
+
+    // eager mode: put the contiguous end-of-tile filter state back after windows were (re-)made out of order
+    auto restore_tile_end = [&]() {
+        __syncwarp();
+        if (lane == 0 && !lazy_fm) {
+            sm.fm_pos = sm.tile_end_pos;
+            sm.fm_y = sm.tile_end_y;
+            sm.fm_xf = sm.tile_end_xf;
+        }
+        __syncwarp();
+    };
+
+    // ---- deferred carrier estimate: log of updating samples ---------------------------------
+    // Entries are runs of consecutive updating samples (relative to the package start).  The open entry
+    // lives in registers (warp-uniform); closed ones go to the stream's log in global memory.
+    auto f1_fold = [&]() { // everything logged so far into the exact value d.ook_f1
+        int g = f1_evaluate<SS>(jb, sm, log, d.start_abs, d.ook_f1, log_n, log_start, log_count);
+        restore_tile_end();
+        d.ook_f1 = g;
+        log_n = 0;
+        log_count = 0;
+    };
+    auto log_append = [&](unsigned long long pos, unsigned cnt) {
+        unsigned rel = (unsigned)(pos - d.start_abs);
+        if (log_count && log_start + log_count == rel) {
+            log_count += cnt;
+            return;
+        }
+        if (log_count) { // close the open entry
+            if (log_n == kLogCap) {
+                f1_fold();
+            } else {
+                if (lane == 0) {
+                    log[2 * log_n] = log_start;
+                    log[2 * log_n + 1] = log_count;
+                }
+                log_n += 1;
+            }
+        }
+        log_start = rel;
+        log_count = cnt;
+    };
+    auto log_clear = [&]() { log_n = log_count = 0; };
+
+    auto emit = [&](int type, unsigned long long pos, bool flush) {
+        if (type == 1 && (log_n || log_count)) f1_fold(); // the carrier estimate of an OOK package is read now
+        log_clear();
+        PackageHeader h = package_header(d, type);
+        unsigned cnt = h.num_pulses + 1 < (unsigned)kMaxPulses ? h.num_pulses + 1 : (unsigned)kMaxPulses;
+        unsigned idx = 0, off = 0;
+        if (lane == 0) {
+            idx = atomicAdd(&p.counters[0], 1u);
+            off = atomicAdd(&p.counters[1], cnt);
+        }
+        idx = __shfl_sync(0xffffffffu, idx, 0);
+        off = __shfl_sync(0xffffffffu, off, 0);
+        bool fits = idx < p.pkg_cap && (unsigned long long)off + cnt <= p.pool_cap;
+        if (!fits) {
+            if (lane == 0) atomicOr(&p.counters[2], 1u);
+        } else {
+            __syncwarp();
+            int const *sp = type == 1 ? tr.ook_pulse : tr.fsk_pulse;
+            int const *sg = type == 1 ? tr.ook_gap : tr.fsk_gap;
+            for (unsigned i = lane; i < cnt; i += 32) {
+                p.pulse_pool[off + i] = sp[i];
+                p.gap_pool[off + i] = sg[i];
+            }
+            if (lane == 0) {
+                unsigned long long blk = flush ? (N + p.block_samples - 1) / p.block_samples : pos / p.block_samples;
+                unsigned long long bstart = blk * p.block_samples;
+                unsigned long long blen = flush ? 0 : (N - bstart < p.block_samples ? N - bstart : p.block_samples);
+                r433b_package k;
+                k.stream = s;
+                k.seq = seq;
+                k.type = type;
+                k.block = (int)blk;
+                k.offset = h.offset;
+                k.end_pos = pos;
+                k.start_ago = flush ? (unsigned)(N - h.start_abs) : (unsigned)(bstart + blen - h.start_abs);
+                k.end_ago = flush ? 0u : (unsigned)(blen - (pos - bstart));
+                k.num_pulses = h.num_pulses;
+                k.pulse_off = off;
+                k.pulse_count = cnt;
+                k.ook_low_estimate = h.low;
+                k.ook_high_estimate = h.high;
+                k.fsk_f1_est = h.f1;
+                k.fsk_f2_est = h.f2;
+                k.first_pair = 0;
+                p.pkgs[idx] = k;
+            }
+        }
+        seq++;
+    };
+
+    int const a1 = p.lpf_a1, b0 = p.lpf_b0;
+
+    for (unsigned long long t0 = p.sample_begin; t0 < p.sample_end && t0 < N; t0 += T) {
+        unsigned long long const remain = N - t0;
+        int const nv_tile = remain < (unsigned long long)T ? (int)remain : T;
+
+        // ---- AM front ---------------------------------------------------------------------------
+        // The (warp-uniform) detector state is not needed here: park it so the loops have the registers.
+        if (lane == 0) sm.park = d;
+        __syncwarp();
+        {
+            int const base = lane * C;
+            int nv = nv_tile - base;
+            nv = nv < 0 ? 0 : (nv > C ? C : nv);
+            uint32_t *const mine = sm.am + lane * kAmStride;
+            unsigned long long const gpos = t0 + (unsigned long long)base; // first sample of the chunk in the stream
+            // the reference keeps x[-1] as int16 across block calls (src/baseband.c:167)
+            int const x_carry = (t0 % p.block_samples == 0) ? (int)(int16_t)x_prev : x_prev;
+            int y, xp;
+            bool const exact = lane == 0;
+            if (exact) {
+                y = y_am;
+                xp = x_carry;
+            } else if (nv > 0) {
+                // guess: the filter has (almost) unit gain, its state is near the local envelope
+                uint32_t rw[4];
+                int x[SPL];
+                load_group<SS>(src, gpos - kWarmAm - SPL, SPL, p.flip, rw);
+                env_group<SS>(rw, p.use_mag, x);
+                xp = x[SPL - 1];
+                y = (x[SPL - 1] + x[SPL - 2]) >> 1;
+                if (y > 32767) y = 32767;
+#pragma unroll 1
+                for (int g = -kWarmAm; g < 0; g += SPL) {
+                    load_group<SS>(src, gpos + g, SPL, p.flip, rw);
+                    env_group<SS>(rw, p.use_mag, x);
+#pragma unroll
+                    for (int j = 0; j < SPL; ++j) {
+                        y = iir16_nowrap(y, a1, b0, x[j] + xp);
+                        xp = x[j];
+                    }
+                }
+            } else {
+                y = 0;
+                xp = 0;
+            }
+            int const y_b = y, xp_b = xp;
+            int y_end = y, xp_end = xp, cmin = 32767, cmax = 0;
+            int16_t *const am_dump = p.am_out ? p.am_out + byte0 / SS + gpos : nullptr;
+            // verify / redo loop: a lane's state at its chunk boundary must be what its left neighbour ended
+            // with (lane 0 starts from the carried exact state); the lowest lane that fails runs its chunk
+            // again from that exact state.  cmin / cmax only ever widen: they stay bounds.
+            int ys = y_b;
+            bool run = true, fixed = false;
+            for (;;) {
+                if (run) {
+                    int yy = ys, xx = xp_b;
+                    int k = 0;
+#pragma unroll 1
+                    for (; k + SPL <= nv; k += SPL) {
+                        uint32_t rw[4];
+                        int x[SPL];
+                        load_group<SS>(src, gpos + k, SPL, p.flip, rw);
+                        env_group<SS>(rw, p.use_mag, x);
+#pragma unroll
+                        for (int j = 0; j < SPL; j += 2) {
+                            int ya = iir16_nowrap(yy, a1, b0, x[j] + xx);
+                            int yb = iir16_nowrap(ya, a1, b0, x[j + 1] + x[j]);
+                            xx = x[j + 1];
+                            yy = yb;
+                            cmin = min(cmin, min(ya, yb));
+                            cmax = max(cmax, max(ya, yb));
+                            mine[(k + j) >> 1] = (uint32_t)ya | ((uint32_t)yb << 16);
+                            if (am_dump) {
+                                am_dump[k + j] = (int16_t)ya;
+                                am_dump[k + j + 1] = (int16_t)yb;
+                            }
+                        }
+                    }
+                    if (k < nv) { // ragged end of the stream
+                        uint32_t rw[4];
+                        int x[SPL];
+                        load_group<SS>(src, gpos + k, nv - k, p.flip, rw);
+                        env_group<SS>(rw, p.use_mag, x);
+                        uint16_t *m16 = reinterpret_cast<uint16_t *>(mine);
+                        for (int j = 0; k + j < nv; ++j) {
+                            yy = iir16_nowrap(yy, a1, b0, x[j] + xx);
+                            xx = x[j];
+                            cmin = min(cmin, yy);
+                            cmax = max(cmax, yy);
+                            m16[k + j] = (uint16_t)yy;
+                            if (am_dump) am_dump[k + j] = (int16_t)yy;
+                        }
+                    }
+                    y_end = yy;
+                    xp_end = xx;
+                }
+                int prev_end = __shfl_up_sync(0xffffffffu, y_end, 1);
+                bool ok = exact || fixed || nv == 0 || y_b == prev_end;
+                unsigned bad = __ballot_sync(0xffffffffu, !ok);
+                if (!bad) break;
+                int const f = __ffs(bad) - 1; // lanes below f are exact
+                ys = __shfl_sync(0xffffffffu, y_end, f - 1);
+                run = lane == f;
+                if (run) {
+                    fixed = true;
+                    atomicAdd(&p.counters[4], 1u);
+                }
+            }
+            sm.cmin[lane] = nv > 0 ? cmin : 32767;
+            sm.cmax[lane] = nv > 0 ? cmax : 0;
+            int const last_lane = (nv_tile - 1) / C;
+            y_am = __shfl_sync(0xffffffffu, y_end, last_lane);
+            x_prev = __shfl_sync(0xffffffffu, xp_end, last_lane);
+        }
+        __syncwarp();
+        // ---- FM for the whole tile when it cannot be made on demand -----------------------------
+        if (!lazy_fm || (!fm_on && p.fm_out)) {
+            for (int w = 0; w * kFmWin < nv_tile; ++w) {
+                if (lane == 0) {
+                    sm.tile_state_y[w] = sm.fm_y;
+                    sm.tile_state_xf[w] = sm.fm_xf;
+                }
+                __syncwarp();
+                int n = nv_tile - w * kFmWin < kFmWin ? nv_tile - w * kFmWin : kFmWin;
+                fm_window<SS>(jb, sm, t0 + (unsigned long long)w * kFmWin, n);
+            }
+            if (lane == 0) {
+                sm.tile_end_pos = sm.fm_pos;
+                sm.tile_end_y = sm.fm_y;
+                sm.tile_end_xf = sm.fm_xf;
+            }
+            __syncwarp();
+        }
+        d = sm.park;
+
+        // FM of tile sample n: make the window that holds it current first
+        auto fm_need = [&](int n) {
+            unsigned long long pos = t0 + (unsigned long long)n;
+            if (sm.win_n > 0 && pos >= sm.win0 && pos < sm.win0 + (unsigned long long)sm.win_n) return;
+            fm_for_walk<SS>(jb, sm, pos, t0, nv_tile, lazy_fm);
+        };
+        auto am_at = [&](int n) -> int { return (int)am16[(n >> 6) * (2 * kAmStride) + (n & 63)]; };
+        auto fm_at = [&](int n) -> int { return (int)(int16_t)sm.fm[fm_pidx((int)(t0 + (unsigned long long)n - sm.win0))]; };
+
+        // ---- package detector over the tile (warp-uniform) -------------------------------
+        if (t0 % p.block_samples == 0) det_call_boundary(d, p.lv);
+        int pend_type = 0; // a package to hand over (set by the GAP scan or by det_step), at stream position pend_pos
+        unsigned long long pend_pos = 0;
+
+        // IDLE over a long stretch, lane-parallel: see the comment in the file header and below.
+        // While |am - low| < 1024 the tracker is low += (am > low) ? +1 : -1, so low keeps the parity of
+        // (low0 + samples seen) and two trajectories of equal parity never cross and merge once the data
+        // passes between them: lane l takes chunk l, starts from a bracket [lo, hi] of the right parity that
+        // provably contains the true value, pushes both ends through its chunk and hands them to the next
+        // lane until every bracket has collapsed.  Chunks in which a trigger is conceivable (or
+        // |am - low| could reach 1024) end the stretch.
+        auto idle_tile = [&](int n) -> int {
+            if (nv_tile - n < 2 * C) return 0;
+            {
+                int hs = p.lv.ratio * d.low;
+                if (hs < p.lv.min_high) hs = p.lv.min_high;
+                if (d.high != hs) return 0;
+            }
+            int const c0 = n / C;
+            int const k0 = lane == c0 ? n - c0 * C : 0;
+            int k1 = nv_tile - lane * C;
+            k1 = k1 > C ? C : k1;
+            bool const in_region = lane >= c0 && k1 > k0;
+            // bounds of the chunk's AM values (of the whole chunk for the first, partial one: still bounds)
+            int const cmin = in_region ? sm.cmin[lane] : 32767, cmax = in_region ? sm.cmax[lane] : -32768;
+            int pmin = cmin, pmax = cmax; // over chunks c0..lane
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                int t1 = __shfl_up_sync(0xffffffffu, pmin, o);
+                int t2 = __shfl_up_sync(0xffffffffu, pmax, o);
+                if (lane >= o) {
+                    pmin = t1 < pmin ? t1 : pmin;
+                    pmax = t2 > pmax ? t2 : pmax;
+                }
+            }
+            int Lmin = d.low < pmin - 1 ? d.low : pmin - 1;
+            int Lmax = d.low > pmax ? d.low : pmax;
+            int hmin = p.lv.ratio * Lmin;
+            if (hmin < p.lv.min_high) hmin = p.lv.min_high;
+            Thresholds th = det_thresholds(Lmin, hmin, p.lv);
+            bool const armed = d.lead_in + (nv_tile - n) > kLeadIn;
+            bool ok = in_region && !(armed && cmax > th.up) && (pmax - Lmin < 1024) && (Lmax - pmin < 1024);
+            unsigned bad = ~__ballot_sync(0xffffffffu, ok) & (0xffffffffu << c0);
+            int const e = bad ? __ffs(bad) - 1 : 32; // chunks c0 .. e-1 form the stretch
+            if (e - c0 < 2) return 0;
+            int const RLmin = __shfl_sync(0xffffffffu, Lmin, e - 1);
+            int const RLmax = __shfl_sync(0xffffffffu, Lmax, e - 1);
+            bool const act = lane >= c0 && lane < e;
+            int const par = (d.low + (lane * C + k0 - n)) & 1; // parity of the true value at this lane's start
+            // Start bracket.  Over K samples whose values lie in [m, M] the tracker climbs one per sample
+            // until it is >= m - 1 and falls one per sample until it is <= M, so from any start in [A, B] it
+            // ends in [min(A + K, m - 1), max(B - K, M)].  The chunk to the left has K = 64 samples (the first
+            // chunk of the stretch may be partial: then the exact start value and its real length are used).
+            int m1 = __shfl_up_sync(0xffffffffu, cmin, 1), M1 = __shfl_up_sync(0xffffffffu, cmax, 1);
+            int K1 = __shfl_up_sync(0xffffffffu, k1 - k0, 1);
+            int lo, hi;
+            if (lane == c0 + 1) {
+                lo = d.low + K1 < m1 - 1 ? d.low + K1 : m1 - 1;
+                hi = d.low - K1 > M1 ? d.low - K1 : M1;
+            } else {
+                lo = RLmin + K1 < m1 - 1 ? RLmin + K1 : m1 - 1;
+                hi = RLmax - K1 > M1 ? RLmax - K1 : M1;
+            }
+            lo = lo < RLmin ? RLmin : lo;
+            hi = hi > RLmax ? RLmax : hi;
+            lo -= (lo - par) & 1;
+            hi += (hi - par) & 1;
+            if (lane == c0) lo = hi = d.low;
+            uint16_t const *chunk = am16 + lane * (2 * kAmStride);
+            int result = 0;
+            bool done = false;
+#pragma unroll 1
+            for (int round = 0; round < 6; ++round) {
+                int elo = lo, ehi = hi;
+                if (act) {
+                    if (elo == ehi) {
+#pragma unroll 4
+                        for (int k = k0; k < k1; ++k) elo += (int)chunk[k] > elo ? 1 : -1;
+                        ehi = elo;
+                    } else {
+#pragma unroll 4
+                        for (int k = k0; k < k1; ++k) {
+                            int a = (int)chunk[k];
+                            elo += a > elo ? 1 : -1;
+                            ehi += a > ehi ? 1 : -1;
+                        }
+                    }
+                }
+                // the true value lies inside every bracket: collapsed end brackets are the true values
+                if (__all_sync(0xffffffffu, !act || elo == ehi)) {
+                    result = __shfl_sync(0xffffffffu, elo, e - 1);
+                    done = true;
+                    break;
+                }
+                int nlo = __shfl_up_sync(0xffffffffu, elo, 1);
+                int nhi = __shfl_up_sync(0xffffffffu, ehi, 1);
+                if (act && lane != c0) {
+                    lo = nlo;
+                    hi = nhi;
+                }
+            }
+            if (!done) return 0;
+            int const len = (e * C < nv_tile ? e * C : nv_tile) - n;
+            d.low = result;
+            int hh = p.lv.ratio * d.low;
+            d.high = hh < p.lv.min_high ? p.lv.min_high : hh;
+            int li = d.lead_in + len;
+            d.lead_in = li > kLeadIn + 1 ? kLeadIn + 1 : li;
+            return len;
+        };
+
+        // IDLE: only the noise-floor tracker moves (src/pulse_detect.c:325-334).  While
+        // |am - low| < 1024 it is low += (am > low) ? +1 : -1; with q = low + j that is
+        // q += 2 * (am_j + j > q): two dependent instructions per sample.
+        auto idle_fast = [&](int n) -> int {
+            int cnt = nv_tile - n < 32 ? nv_tile - n : 32;
+            int hs = p.lv.ratio * d.low;
+            if (hs < p.lv.min_high) hs = p.lv.min_high;
+            if (d.high != hs) return 0; // first IDLE sample after a package: not yet re-derived
+            int a = lane < cnt ? am_at(n + lane) : -32768;
+            int lmin = d.low - cnt;
+            int hmin = p.lv.ratio * lmin;
+            if (hmin < p.lv.min_high) hmin = p.lv.min_high;
+            Thresholds th = det_thresholds(lmin, hmin, p.lv); // lowest trigger level reachable in this chunk
+            bool armed = d.lead_in + cnt - 1 > kLeadIn;
+            bool stop = lane < cnt && ((armed && a > th.up) || (a - lmin >= 1024) || (d.low + cnt - a >= 1024));
+            unsigned m = __ballot_sync(0xffffffffu, stop);
+            if (m) {
+                int first = __ffs(m) - 1;
+                cnt = first < cnt ? first : cnt;
+            }
+            if (cnt == 0) return 0;
+            __syncwarp();
+            sm.q[lane] = a + lane;
+            __syncwarp();
+            int q = d.low;
+            int j = 0;
+            for (; j + 4 <= cnt; j += 4) {
+                int4 const b = *reinterpret_cast<int4 const *>(&sm.q[j]);
+                if (b.x > q) q += 2;
+                if (b.y > q) q += 2;
+                if (b.z > q) q += 2;
+                if (b.w > q) q += 2;
+            }
+            for (; j < cnt; ++j)
+                if (sm.q[j] > q) q += 2;
+            d.low = q - cnt;
+            int hh = p.lv.ratio * d.low;
+            d.high = hh < p.lv.min_high ? p.lv.min_high : hh;
+            int li = d.lead_in + cnt;
+            d.lead_in = li > kLeadIn + 1 ? kLeadIn + 1 : li;
+            return cnt;
+        };
+
+        // GAP: thresholds are frozen; the next event is the first sample above `up` or the run length
+        // reaching an end-of-package limit (src/pulse_detect.c:422-470).  Look for either in the rest of the
+        // tile, 32 samples per ballot.
+        auto gap_fast = [&](int n) -> int {
+            if (d.eop_flag) return 0;
+            int const cnt = nv_tile - n;
+            Thresholds th = det_thresholds(d.low, d.high, p.lv);
+            long long lim_a = 10ll * d.longest > 10ll * per_ms ? 10ll * d.longest : 10ll * per_ms;
+            long long lim_b = 100ll * per_ms;
+            long long rstar = (lim_a < lim_b ? lim_a : lim_b) + 1; // first run length that ends the package
+            long long je = rstar - d.run - 1;
+            if (je < 0) je = 0;
+            int const horizon = je < cnt ? (int)je + 1 : cnt; // samples that matter
+            int ja = 0x7fffffff;
+#pragma unroll 1
+            for (int base = 0; base < horizon; base += 32) {
+                int a = base + lane < cnt ? am_at(n + base + lane) : -32768;
+                unsigned m = __ballot_sync(0xffffffffu, a > th.up);
+                if (m) {
+                    ja = base + __ffs(m) - 1;
+                    break;
+                }
+            }
+            if (ja < cnt && ja <= je) { // a new pulse starts first
+                d.run += ja + 1;
+                put(tr.ook_gap, d.ook_hw, d.ook_n, d.run);
+                d.ook_n += 1;
+                if (d.ook_n >= (unsigned)kMaxPulses) {
+                    d.st = kIdle;
+                    pend_type = 1;
+                    pend_pos = t0 + (unsigned long long)(n + ja);
+                    return ja; // that sample is looked at again in IDLE
+                }
+                d.run = 0;
+                d.st = kPulse;
+                return ja + 1;
+            }
+            if (je < cnt) { // end of package by gap length
+                d.run += (int)je + 1;
+                put(tr.ook_gap, d.ook_hw, d.ook_n, d.run);
+                d.ook_n += 1;
+                d.st = kIdle;
+                pend_type = 1;
+                pend_pos = t0 + (unsigned long long)(n + (int)je);
+                return (int)je;
+            }
+            d.run += cnt;
+            return cnt;
+        };
+
+        // PULSE after the first pulse: the high-level estimator (src/pulse_detect.c:362-363) is a truncating
+        // 64-sample moving average -- inherently sequential -- but the pulse only ends on a sample below the
+        // threshold its value implies.  One step never lifts `high` above max(high, 64 * (am / 64) + 63), so
+        // the largest am of the chunk bounds every threshold of the chunk from above: samples not below THAT
+        // threshold cannot end the pulse.  The recurrence runs over exactly those (operands staged in shared
+        // memory, four per load); the carrier estimate of those samples is deferred (logged).  The first
+        // sample that might end the pulse is left to det_step(), which tests it exactly.
+        auto pulse_fast = [&](int n) -> int {
+            int cnt = nv_tile - n < 32 ? nv_tile - n : 32;
+            if (!defer_f1) { // FM is read here: stay inside the current window
+                int const in_win = (int)(sm.win0 + (unsigned long long)sm.win_n - (t0 + (unsigned long long)n));
+                cnt = cnt < in_win ? cnt : in_win;
+            }
+            int a = lane < cnt ? am_at(n + lane) : 32767;
+            int aq = a >> 6; // am >= 0
+            int const top = __reduce_max_sync(0xffffffffu, lane < cnt ? aq : 0); // one REDUX each
+            int const bot = __reduce_min_sync(0xffffffffu, aq);
+            int hmax = 64 * top + 63;
+            hmax = d.high > hmax ? d.high : hmax;
+            Thresholds th = det_thresholds(d.low, hmax, p.lv);
+            unsigned m = __ballot_sync(0xffffffffu, lane < cnt && a < th.down);
+            if (m) cnt = __ffs(m) - 1;
+            if (cnt == 0) return 0;
+            __syncwarp();
+            sm.q[lane] = aq;
+            __syncwarp();
+            int h = d.high; // h >= min_high >= 0 here, so h / 64 == h >> 6
+            int const minh = p.lv.min_high;
+            int j = 0;
+            if (64 * bot >= minh + 64) { // h - h/64 + q >= minh for every q >= bot when h >= minh: no clamp needed
+                for (; j + 4 <= cnt; j += 4) {
+                    int4 const b = *reinterpret_cast<int4 const *>(&sm.q[j]);
+                    h += b.x - (int)((unsigned)h >> 6);
+                    h += b.y - (int)((unsigned)h >> 6);
+                    h += b.z - (int)((unsigned)h >> 6);
+                    h += b.w - (int)((unsigned)h >> 6);
+                }
+            }
+            for (; j < cnt; ++j) {
+                h += sm.q[j] - (int)((unsigned)h >> 6);
+                h = h < minh ? minh : h;
+            }
+            d.high = h;
+            if (defer_f1) {
+                log_append(t0 + (unsigned long long)n, (unsigned)cnt);
+            } else {
+                int f = lane < cnt ? fm_at(n + lane) : 0;
+                int g = d.ook_f1;
+#pragma unroll 1
+                for (int k = 0; k < cnt; ++k) g = f1_step(g, __shfl_sync(0xffffffffu, f, k));
+                d.ook_f1 = g;
+            }
+            d.run += cnt;
+            return cnt;
+        };
+
+        // PULSE of the FIRST pulse: the same bound, with the FSK sub-detector and the (not yet deferred)
+        // carrier estimate fed in the loop (src/pulse_detect.c:362-371).  An FSK transmission is one long OOK
+        // "pulse", so this is the hot loop of FSK captures.  Needs FM: stays inside the current window.
+        auto pulse0_fast = [&](int n) -> int {
+            int cnt = nv_tile - n < 32 ? nv_tile - n : 32;
+            int const in_win = (int)(sm.win0 + (unsigned long long)sm.win_n - (t0 + (unsigned long long)n));
+            cnt = cnt < in_win ? cnt : in_win;
+            int a = lane < cnt ? am_at(n + lane) : 32767;
+            int f = lane < cnt ? fm_at(n + lane) : 0;
+            int aq = a >> 6;
+            int const top = __reduce_max_sync(0xffffffffu, lane < cnt ? aq : 0);
+            int hmax = 64 * top + 63;
+            hmax = d.high > hmax ? d.high : hmax;
+            Thresholds th = det_thresholds(d.low, hmax, p.lv);
+            unsigned m = __ballot_sync(0xffffffffu, lane < cnt && a < th.down);
+            if (m) cnt = __ffs(m) - 1;
+            if (cnt == 0) return 0;
+            int const minh = p.lv.min_high;
+#pragma unroll 1
+            for (int j = 0; j < cnt; ++j) {
+                int aj = __shfl_sync(0xffffffffu, aq, j);
+                int fj = __shfl_sync(0xffffffffu, f, j);
+                d.high += aj - (int)((unsigned)d.high >> 6);
+                d.high = d.high < minh ? minh : d.high;
+                d.ook_f1 += fj / 64 - d.ook_f1 / 64;
+                if (p.fpdm == 0)
+                    fsk_classic(d, tr, fj, cx);
+                else
+                    fsk_minmax(d, tr, fj, cx);
+            }
+            d.run += cnt;
+            return cnt;
+        };
+
+        // GAP_START after the first pulse (no FSK feed): thresholds are frozen and nothing happens until
+        // either a sample rises above `up` (spurious gap) or the run reaches 10 samples.  Skip the uneventful
+        // samples in front of that transition; det_step() takes the transition.
+        auto gapstart_fast = [&](int n) -> int {
+            int quiet = kMinPulseSamples - 1 - d.run; // samples that can pass without reaching 10
+            if (quiet <= 0) return 0;
+            int cnt = nv_tile - n < quiet ? nv_tile - n : quiet;
+            Thresholds th = det_thresholds(d.low, d.high, p.lv);
+            int a = lane < cnt ? am_at(n + lane) : -32768;
+            unsigned m = __ballot_sync(0xffffffffu, lane < cnt && a > th.up);
+            if (m) {
+                int ja = __ffs(m) - 1;
+                cnt = ja < cnt ? ja : cnt;
+            }
+            d.run += cnt;
+            return cnt;
+        };
+
+        for (int n = 0; n < nv_tile;) {
+            // inside a first pulse (and its GAP_START) the FSK sub-detector and the undeferred estimate read FM
+            bool const first = d.ook_n == 0 && (d.st == kPulse || d.st == kGapStart);
+            bool const wants_fm = first || (d.st == kPulse && !defer_f1);
+            if (wants_fm) fm_need(n);
+            int adv = 0;
+            if (d.st == kIdle) {
+                adv = idle_tile(n);
+                if (!adv) adv = idle_fast(n);
+            } else if (d.st == kGap) {
+                adv = gap_fast(n);
+            } else if (d.st == kPulse) {
+                adv = d.ook_n ? pulse_fast(n) : pulse0_fast(n);
+            } else if (d.ook_n) {
+                adv = gapstart_fast(n);
+            }
+            if (!adv && !pend_type) {
+                // every lane runs the (warp-uniform) step and writes the same train entries: keep the lanes
+                // together so that no lane reads an entry another lane has already overwritten for a later sample
+                __syncwarp();
+                int const a = am_at(n);
+                int r;
+                if (first)
+                    r = det_step<kStepFirst>(d, p.lv, tr, a, fm_at(n), t0 + n, per_ms, p.fpdm, cx, defer_f1);
+                else
+                    r = det_step<kStepLean>(d, p.lv, tr, a, wants_fm ? fm_at(n) : 0, t0 + n, per_ms, p.fpdm, cx, defer_f1);
+                if (r & kStepF1Deferred) log_append(t0 + (unsigned long long)n, 1u);
+                if (r & 3) {
+                    pend_type = r & 3; // the same sample is examined again, now in IDLE
+                    pend_pos = t0 + (unsigned long long)n;
+                } else {
+                    if (d.st == kPulse && d.run == 0 && d.ook_n == 0) log_clear(); // a package has just begun
+                    adv = 1;
+                }
+            }
+            if (pend_type) {
+                emit(pend_type, pend_pos, false);
+                det_call_boundary(d, p.lv);
+                pend_type = 0;
+            }
+            n += adv;
+        }
+        __syncwarp();
+    }
+
+    // flush_sdr_flow(): len == 0 call(s) at the end of the file, in the launch that reaches it
+    if (N <= p.sample_end && !flushed) {
+        for (;;) {
+            int ev = det_flush(d, tr, p.fpdm);
+            if (!ev) break;
+            emit(ev, N, true);
+        }
+        flushed = 1;
+    }
+    __syncwarp();
+    if (lane == 0 && p.state) {
+        StreamState &ss = p.state[s];
+        ss.d = d;
+        ss.y_am = y_am;
+        ss.x_prev = x_prev;
+        ss.fm_pos = sm.fm_pos;
+        ss.fm_y = sm.fm_y;
+        ss.fm_xf = sm.fm_xf;
+        ss.log_n = log_n;
+        ss.last_start = log_start;
+        ss.last_count = log_count;
+        ss.seq = seq;
+        ss.flushed = flushed;
+    }
+}
+
+} // namespace r433b

@@ -15,15 +15,18 @@ rep, which = sys.argv[1], sys.argv[2]
 n_samples = float(sys.argv[3]) if len(sys.argv) > 3 else 4096.0 * (1 << 20)
 
 MARKS = {
-    "detect": ("r433b_kernels.cuh", [
-        ("load_group", "void load_group"), ("fm_make (FM on demand)", "FmCarry fm_make("), ("prologue", "k_detect(DetectParams p)"),
-        ("emit", "auto emit = [&]"), ("tile loop top", "for (unsigned long long t0 = p.sample_begin"),
-        ("front: maps", "auto front = [&](auto with_fm)"), ("front: IIR rounds", "// phase 2: the low-pass(es), exact and lane-parallel"),
-        ("front: final pass", "// phase 3: final pass from the exact state"), ("park / choose front", "// d.st != IDLE at a tile start implies"),
+    "detect": ("r433b_detect.cuh", [
+        ("load_group / env_group", "void load_group"), ("fm: discriminator (disc_fill)", "void disc_fill("),
+        ("fm: state rebuild (fm_cold)", "void fm_cold("), ("fm: window low-pass (fm_window)", "void fm_window("),
+        ("fm: demand", "void fm_demand("), ("deferred carrier estimate (f1_evaluate)", "int f1_step("),
+        ("prologue", "k_detect(DetectParams p)"), ("log_append", "auto log_append = [&]"), ("emit", "auto emit = [&]"),
+        ("tile loop top / AM warm-up", "for (unsigned long long t0 = p.sample_begin"),
+        ("AM chunk pass + verify", "// verify / redo loop: a lane's state at its chunk boundary"),
+        ("tile FM pass / fm_need", "// ---- FM for the whole tile when it cannot be made on demand"),
         ("idle_tile", "auto idle_tile = [&]"), ("idle_fast", "auto idle_fast = [&]"), ("gap_fast", "auto gap_fast = [&]"),
         ("pulse_fast", "auto pulse_fast = [&]"), ("pulse0_fast (first pulse + FSK)", "auto pulse0_fast = [&]"),
-        ("gapstart_fast", "auto gapstart_fast = [&]"), ("walk loop + det_step call", "// The detector walks the tile until"),
-        ("flush / save", "// flush_sdr_flow()"), ("(k_slice)", "k_slice(SliceParams p)")]),
+        ("gapstart_fast", "auto gapstart_fast = [&]"), ("walk loop + det_step call", "for (int n = 0; n < nv_tile;) {"),
+        ("flush / save", "// flush_sdr_flow()")]),
     "slice": ("r433b_slice.cuh", [
         ("EventWriter", "struct EventWriter"), ("slicer helpers", "struct PulseView"), ("slicer_begin / slicer_step (front end)", "slicer_begin("),
         ("slicer_apply (back end)", "slicer_apply("), ("slice_dispatch loop", "slice_dispatch(")]),
@@ -40,7 +43,8 @@ pos.sort()
 
 out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--print-source", "cuda,sass", "--csv"], capture_output=True, text=True).stdout
 cur, hd = None, None
-reg = collections.defaultdict(lambda: [0.0, 0.0, 0.0])
+reg = collections.defaultdict(lambda: [0.0, 0.0, 0.0, 0])
+last_region = None
 for r in csv.reader(io.StringIO(out)):
     if not r:
         continue
@@ -56,6 +60,9 @@ for r in csv.reader(io.StringIO(out)):
     try:
         ln = int(d["Line No"])
     except ValueError:
+        # a SASS row under the last source line: static code size of the region
+        if last_region is not None and len(r) > 2 and r[2].startswith("0x"):
+            reg[last_region][3] += 1
         continue
 
     def f(k):
@@ -71,14 +78,16 @@ for r in csv.reader(io.StringIO(out)):
                 name = nm
         name = f"{fname}: {name}"
     v = reg[name]
+    last_region = name
     v[0] += f("# Samples")
     v[1] += f("Instructions Executed")
     v[2] += f("Thread Instructions Executed")
 ts, ti = sum(v[0] for v in reg.values()), sum(v[1] for v in reg.values())
-print("| region | stall samples | warp instructions | warp-instr / IQ sample | avg active lanes |")
-print("|---|---|---|---|---|")
-for k, (s, i, t) in sorted(reg.items(), key=lambda kv: -kv[1][1]):
-    if i / ti < 0.002:
+print("| region | stall samples | warp instructions | warp-instr / IQ sample | avg active lanes | SASS instructions (static) |")
+print("|---|---|---|---|---|---|")
+for k, (s, i, t, c) in sorted(reg.items(), key=lambda kv: -kv[1][1]):
+    if i / ti < 0.002 and c < 200:
         continue
-    print(f"| {k} | {100 * s / ts:.1f} % | {100 * i / ti:.1f} % | {i / n_samples:.2f} | {t / max(i, 1):.1f} |")
+    print(f"| {k} | {100 * s / ts:.1f} % | {100 * i / ti:.1f} % | {i / n_samples:.2f} | {t / max(i, 1):.1f} | {c} |")
+print(f"\nstatic code: {sum(v[3] for v in reg.values())} SASS instructions = {sum(v[3] for v in reg.values()) * 16 / 1024:.0f} KiB")
 print(f"\ntotal (source view): {ti / n_samples:.2f} warp instructions per IQ sample")
