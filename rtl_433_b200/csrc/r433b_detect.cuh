@@ -787,11 +787,16 @@ __global__ void __launch_bounds__(kDetectWarps * 32, kDetectCtasPerSm) k_detect(
                 // guess: the filter has (almost) unit gain, its state is near the local envelope
                 uint32_t rw[4];
                 int x[SPL];
-                load_group<SS>(src, gpos - kWarmAm - SPL, SPL, p.flip, rw);
-                env_group<SS>(rw, p.use_mag, x);
-                xp = x[SPL - 1];
-                y = (x[SPL - 1] + x[SPL - 2]) >> 1;
-                if (y > 32767) y = 32767;
+                if (gpos >= (unsigned long long)(kWarmAm + SPL)) {
+                    load_group<SS>(src, gpos - kWarmAm - SPL, SPL, p.flip, rw);
+                    env_group<SS>(rw, p.use_mag, x);
+                    xp = x[SPL - 1];
+                    y = (x[SPL - 1] + x[SPL - 2]) >> 1;
+                    if (y > 32767) y = 32767;
+                } else { // the warm-up begins at sample 0 of the stream (gpos == kWarmAm): the reset state, exact
+                    xp = 0;
+                    y = 0;
+                }
 #pragma unroll 1
                 for (int g = -kWarmAm; g < 0; g += SPL) {
                     load_group<SS>(src, gpos + g, SPL, p.flip, rw);

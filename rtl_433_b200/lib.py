@@ -30,8 +30,7 @@ EXPORTS = ["r433b_create", "r433b_destroy", "r433b_last_error", "r433b_set_level
 
 def build(force=False, verbose=False):
     """nvcc -> csrc/libr433b.so for sm_100a (cross-compiles without a GPU)."""
-    srcs = [os.path.join(CSRC, n) for n in ("r433b_api.cu", "r433b_kernels.cuh", "r433b_core.cuh", "r433b_slice.cuh",
-                                             "r433b_host.hpp")]
+    srcs = [os.path.join(CSRC, n) for n in sorted(os.listdir(CSRC)) if n.endswith((".cu", ".cuh", ".hpp"))]
     srcs += [os.path.join(os.path.dirname(HERE), "include", n) for n in ("r433b.h", "r433b_abi.h")]
     if not force and os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(s) for s in srcs):
         return LIB_PATH

@@ -4,6 +4,17 @@
 // synchronous, events measure nothing.  Only tests ever put this directory on an include path.
 #pragma once
 #include "simt.hpp"
+#include <map>
+#include <sys/mman.h>
+#include <unistd.h>
+
+namespace simt {
+inline std::map<void *, void *> &alloc_table()
+{
+    static std::map<void *, void *> t;
+    return t;
+}
+} // namespace simt
 
 typedef int cudaError_t;
 enum { cudaSuccess = 0, cudaErrorMemoryAllocation = 2 };
@@ -17,14 +28,43 @@ inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
 inline cudaError_t cudaDeviceGetAttribute(int *v, int, int) { *v = 2; return cudaSuccess; } // a 2-SM "GPU": small fixed grids
 inline char const *cudaGetErrorString(cudaError_t) { return "emulated"; }
 inline cudaError_t cudaGetLastError() { return cudaSuccess; }
+// "Device" allocations sit between two inaccessible guard pages (an electric fence): an out-of-bounds access of
+// a kernel faults here instead of passing silently.  The buffer starts on a page boundary right behind the
+// front guard (catches reads in front of an allocation); with SIMT_GUARD=back it ends (rounded up to 16 bytes)
+// right in front of the rear guard instead.
+struct simt_alloc_hdr { void *map; size_t map_len; };
 inline cudaError_t cudaMalloc(void **p, size_t n)
 {
-    *p = aligned_alloc(256, (n + 255) / 256 * 256);
-    if (*p) memset(*p, 0xA5, n); // device memory is not zeroed
-    return *p ? cudaSuccess : cudaErrorMemoryAllocation;
+    static long const page = sysconf(_SC_PAGESIZE);
+    static bool const back = getenv("SIMT_GUARD") && !strcmp(getenv("SIMT_GUARD"), "back");
+    size_t const body = (n + page - 1) / page * page;
+    size_t const len = body + 3 * page; // [header page][guard][body][guard]
+    char *m = (char *)mmap(nullptr, len, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+    if (m == (char *)MAP_FAILED) { *p = nullptr; return cudaErrorMemoryAllocation; }
+    mprotect(m + page, page, PROT_NONE);
+    mprotect(m + 2 * page + body, page, PROT_NONE);
+    char *u = m + 2 * page;
+    if (back) u += (body - n) / 16 * 16;
+    memset(m + 2 * page, 0xA5, body); // device memory is not zeroed
+    simt_alloc_hdr h{m, len};
+    memcpy(m, &h, sizeof(h));
+    simt::alloc_table()[(void *)u] = m;
+    *p = u;
+    return cudaSuccess;
 }
 template <class T> inline cudaError_t cudaMalloc(T **p, size_t n) { return cudaMalloc((void **)p, n); }
-inline cudaError_t cudaFree(void *p) { free(p); return cudaSuccess; }
+inline cudaError_t cudaFree(void *p)
+{
+    if (!p) return cudaSuccess;
+    auto &t = simt::alloc_table();
+    auto it = t.find(p);
+    if (it == t.end()) abort();
+    simt_alloc_hdr h;
+    memcpy(&h, it->second, sizeof(h));
+    t.erase(it);
+    munmap(h.map, h.map_len);
+    return cudaSuccess;
+}
 inline cudaError_t cudaMallocHost(void **p, size_t n) { *p = aligned_alloc(256, (n + 255) / 256 * 256); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
 inline cudaError_t cudaFreeHost(void *p) { free(p); return cudaSuccess; }
 inline cudaError_t cudaMemcpy(void *d, void const *s, size_t n, cudaMemcpyKind) { memcpy(d, s, n); return cudaSuccess; }
