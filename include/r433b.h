@@ -115,6 +115,10 @@ typedef struct r433b_results {
 typedef struct r433b_timing {
     float h2d_ms, detect_ms, slice_ms, d2h_ms, total_ms; /* pipelined batches: kernel sums + wall total only */
     uint32_t detect_launches, slice_launches;
+    float front_ms;          /* k_front (IQ -> AM), not part of detect_ms (the walk, k_detect) */
+    uint32_t front_launches;
+    uint32_t front_redone;   /* 64-sample chunks k_front ran twice (its guess of the filter state did not verify) */
+    uint32_t front_repairs;  /* tiles whose start k_detect recomputed (k_front's guess for the tile did not fit) */
 } r433b_timing;
 
 int r433b_create(int cuda_device, r433b_ctx **out);
@@ -147,6 +151,11 @@ int r433b_get_counts(r433b_ctx const *ctx, uint64_t out[4]);
 
 /* Stage arrays of one stream (batch.want_stages): what dm_state.am_buf / buf.fm held. */
 int r433b_copy_stage(r433b_ctx *ctx, uint32_t stream, int16_t *am, int16_t *fm, uint64_t max_samples);
+
+/* Position-independent 64-bit checksum (FNV-1a over 32-bit words) of everything a fetched batch holds for one
+   stream: package headers, pulse / gap widths, the event bytes of every (package, device) pair.  Streams that
+   carry the same samples have equal digests wherever they sit in a batch. */
+int r433b_stream_digest(r433b_ctx *ctx, r433b_results const *res, uint32_t stream, uint64_t *digest);
 
 /* ---- host-side replay: the part of run_*_demods()/account_event() that stays on the CPU ---- */
 

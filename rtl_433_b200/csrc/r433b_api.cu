@@ -60,6 +60,7 @@ struct r433b_ctx {
     int enable_fm = 0;
     int n_sms = 148;        // cudaDevAttrMultiProcessorCount of `device`
     unsigned stage_words = kStageWords; // R433B_STAGE_WORDS overrides (tuning experiments)
+    int spoil_front = 0; // R433B_SPOIL_FRONT=1|2: k_front starts from wrong guesses (tests of the redo / repair paths)
     int lazy_fm = 1; // R433B_EAGER_FM=1 in the environment turns the on-demand FM path off (A/B checks)
     Levels lv{};
     // device memory (grow only)
@@ -78,8 +79,9 @@ struct r433b_ctx {
     int pipeline_groups = 0; // 0 = automatic, 1 = off
     cudaStream_t s_in = nullptr, s_det = nullptr, s_out = nullptr;
     static constexpr int kMaxGroups = 16;
-    cudaEvent_t ev_in[kMaxGroups]{}, ev_det[kMaxGroups]{}, ev_slc[kMaxGroups]{}, ev_t[4 * kMaxGroups]{}, ev_init = nullptr;
-    DevBuf d_ranges, d_state, d_lengths, d_stage, d_raw, d_log;
+    cudaEvent_t ev_in[kMaxGroups]{}, ev_det[kMaxGroups]{}, ev_slc[kMaxGroups]{}, ev_t[4 * kMaxGroups]{}, ev_f[kMaxGroups]{}, ev_init = nullptr;
+    DevBuf d_ranges, d_state, d_lengths, d_stage, d_raw, d_log, d_amoff, d_chunks;
+    std::vector<uint64_t> am_offsets; // first sample of stream i in d_am (multiples of the tile), n_streams + 1
     HostBuf h_ranges;
     bool d2h_done = false;
 };
@@ -160,9 +162,11 @@ int r433b_create(int cuda_device, r433b_ctx **out)
     for (auto &v : ctx->ev_det) cudaEventCreateWithFlags(&v, cudaEventDisableTiming);
     for (auto &v : ctx->ev_slc) cudaEventCreateWithFlags(&v, cudaEventDisableTiming);
     for (auto &v : ctx->ev_t) cudaEventCreate(&v);
+    for (auto &v : ctx->ev_f) cudaEventCreate(&v);
     cudaEventCreateWithFlags(&ctx->ev_init, cudaEventDisableTiming);
     ctx->lv = compute_levels(0, 0.0f, -12.1442f, 9.0f);
     if (char const *v = getenv("R433B_EAGER_FM")) ctx->lazy_fm = !(v[0] && v[0] != '0');
+    if (char const *v = getenv("R433B_SPOIL_FRONT")) ctx->spoil_front = atoi(v);
     if (char const *v = getenv("R433B_STAGE_WORDS")) ctx->stage_words = (unsigned)std::max(8, atoi(v));
     if (cudaDeviceGetAttribute(&ctx->n_sms, cudaDevAttrMultiProcessorCount, cuda_device) != cudaSuccess || ctx->n_sms <= 0)
         ctx->n_sms = 148;
@@ -176,7 +180,7 @@ void r433b_destroy(r433b_ctx *ctx)
     cudaSetDevice(ctx->device);
     for (DevBuf *b : {&ctx->d_data, &ctx->d_offsets, &ctx->d_train, &ctx->d_pkgs, &ctx->d_ppool, &ctx->d_gpool,
                  &ctx->d_counters, &ctx->d_am, &ctx->d_fm, &ctx->d_devparams, &ctx->d_lists, &ctx->d_pairs,
-                 &ctx->d_arena, &ctx->d_cursor, &ctx->d_ranges, &ctx->d_state, &ctx->d_lengths, &ctx->d_stage, &ctx->d_raw, &ctx->d_log})
+                 &ctx->d_arena, &ctx->d_cursor, &ctx->d_ranges, &ctx->d_state, &ctx->d_lengths, &ctx->d_stage, &ctx->d_raw, &ctx->d_log, &ctx->d_amoff, &ctx->d_chunks})
         if (b->p) cudaFree(b->p);
     for (HostBuf *b : {&ctx->h_pkgs, &ctx->h_ppool, &ctx->h_gpool, &ctx->h_pairs, &ctx->h_events, &ctx->h_ranges})
         if (b->p) cudaFreeHost(b->p);
@@ -186,6 +190,8 @@ void r433b_destroy(r433b_ctx *ctx)
         for (int i = 0; i < r433b_ctx::kMaxGroups; ++i)
             if (arr[i]) cudaEventDestroy(arr[i]);
     for (auto &v : ctx->ev_t)
+        if (v) cudaEventDestroy(v);
+    for (auto &v : ctx->ev_f)
         if (v) cudaEventDestroy(v);
     if (ctx->ev_init) cudaEventDestroy(ctx->ev_init);
     for (cudaStream_t st : {ctx->s_in, ctx->s_det, ctx->s_out})
@@ -313,10 +319,18 @@ int r433b_process(r433b_ctx *ctx, r433b_batch const *b)
     if (int r = dev_reserve(ctx, ctx->d_log, (size_t)std::max(1u, b->n_streams) * kLogCap * 2 * sizeof(unsigned))) return r;
     if (int r = dev_reserve(ctx, ctx->d_counters, 64)) return r;
     if (int r = dev_reserve(ctx, ctx->d_cursor, 64)) return r;
-    if (b->want_stages) {
-        if (int r = dev_reserve(ctx, ctx->d_am, total_bytes / SS * sizeof(int16_t) + 16)) return r;
+    // k_front's output: 16-bit AM of every sample, every stream padded to whole tiles, + the bounds of every chunk
+    ctx->am_offsets.resize(b->n_streams + 1);
+    ctx->am_offsets[0] = 0;
+    for (uint32_t i = 0; i < b->n_streams; ++i)
+        ctx->am_offsets[i + 1] = ctx->am_offsets[i] + (ctx->lengths[i] / SS + T - 1) / T * T;
+    uint64_t const am_samples = ctx->am_offsets[b->n_streams];
+    if (int r = dev_reserve(ctx, ctx->d_am, am_samples * sizeof(int16_t) + 16)) return r;
+    if (int r = dev_reserve(ctx, ctx->d_chunks, am_samples / kChunk * sizeof(ChunkInfo) + 16)) return r;
+    if (int r = dev_reserve(ctx, ctx->d_amoff, (b->n_streams + 1) * sizeof(uint64_t))) return r;
+    CU(cudaMemcpy(ctx->d_amoff.p, ctx->am_offsets.data(), (b->n_streams + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice));
+    if (b->want_stages)
         if (int r = dev_reserve(ctx, ctx->d_fm, total_bytes / SS * sizeof(int16_t) + 16)) return r;
-    }
 
     DetectParams dp{};
     dp.data = d_in;
@@ -350,12 +364,43 @@ int r433b_process(r433b_ctx *ctx, r433b_batch const *b)
     dp.train_scratch = (int *)ctx->d_train.p;
     dp.log_scratch = (unsigned *)ctx->d_log.p;
     dp.counters = (unsigned *)ctx->d_counters.p;
-    dp.am_out = b->want_stages ? (int16_t *)ctx->d_am.p : nullptr;
+    dp.am_offsets = (unsigned long long const *)ctx->d_amoff.p;
+    dp.am = (int16_t *)ctx->d_am.p;
+    dp.chunks = (ChunkInfo const *)ctx->d_chunks.p;
+    dp.want_stages = b->want_stages ? 1 : 0;
     dp.fm_out = b->want_stages ? (int16_t *)ctx->d_fm.p : nullptr;
 
-    auto launch_detect = [&](DetectParams const &q, cudaStream_t s) {
+    uint64_t max_samples = 0;
+    for (uint32_t i = 0; i < b->n_streams; ++i) max_samples = std::max<uint64_t>(max_samples, ctx->lengths[i] / SS);
+    // k_front over the tiles [sample_begin, sample_end) of every stream, then the walk over the same range
+    auto launch_detect = [&](DetectParams const &q, cudaStream_t s, cudaEvent_t after_front) {
         unsigned n = q.stream_end - q.stream0;
         if (!n) return;
+        uint64_t const t_end = (std::min<uint64_t>(q.sample_end, max_samples) + T - 1) / T, t_begin = q.sample_begin / T;
+        if (t_end > t_begin) {
+            FrontParams fp{};
+            fp.data = q.data;
+            fp.offsets = q.offsets;
+            fp.lengths = q.lengths;
+            fp.am_offsets = q.am_offsets;
+            fp.n_streams = q.n_streams;
+            fp.tile_begin = t_begin;
+            fp.tiles = (unsigned)(t_end - t_begin);
+            fp.use_mag = q.use_mag;
+            fp.flip = q.flip;
+            fp.block_samples = q.block_samples;
+            fp.a1 = q.lpf_a1;
+            fp.b0 = q.lpf_b0;
+            fp.am = q.am;
+            fp.chunks = (ChunkInfo *)ctx->d_chunks.p;
+            fp.counters = q.counters;
+            fp.spoil = ctx->spoil_front;
+            uint64_t const warps = (uint64_t)q.n_streams * fp.tiles;
+            unsigned const fgrid = (unsigned)((warps + kFrontWarps - 1) / kFrontWarps);
+            void (*ffn)(FrontParams) = SS == 2 ? k_front<2> : k_front<4>;
+            R4_LAUNCH(ffn, fgrid, kFrontWarps * 32, 0, s, fp);
+        }
+        cudaEventRecord(after_front, s);
         unsigned grid = (n + kDetectWarps - 1) / kDetectWarps;
         size_t sm = (size_t)kDetectWarps * sizeof(WarpSmem);
         void (*kfn)(DetectParams) = SS == 2 ? k_detect<2> : k_detect<4>;
@@ -478,7 +523,7 @@ int r433b_process(r433b_ctx *ctx, r433b_batch const *b)
             dg.sample_begin = (uint64_t)g * slice_samples;
             dg.sample_end = g == G - 1 ? ~0ull : (uint64_t)(g + 1) * slice_samples;
             dg.first_chunk = g == 0;
-            launch_detect(dg, ctx->s_det);
+            launch_detect(dg, ctx->s_det, ctx->ev_f[g]);
             CU(cudaEventRecord(ctx->ev_t[4 * g + 1], ctx->s_det));
             R4_LAUNCH(k_mark, 1, 1, 0, ctx->s_det, d_rg + g, 1, d_cnt, d_cur);
             CU(cudaEventRecord(ctx->ev_det[g], ctx->s_det));
@@ -531,14 +576,22 @@ int r433b_process(r433b_ctx *ctx, r433b_batch const *b)
             ctx->n_events = last.events_end;
             ctx->n_samples = used_bytes / SS;
             ctx->d2h_done = d2h_ok;
-            float det = 0, slc = 0;
+            float det = 0, slc = 0, frt = 0;
             for (int g = 0; g < G; ++g) {
-                float a = 0, c = 0;
-                cudaEventElapsedTime(&a, ctx->ev_t[4 * g + 0], ctx->ev_t[4 * g + 1]);
+                float a = 0, c = 0, f = 0;
+                cudaEventElapsedTime(&f, ctx->ev_t[4 * g + 0], ctx->ev_f[g]);
+                cudaEventElapsedTime(&a, ctx->ev_f[g], ctx->ev_t[4 * g + 1]);
                 cudaEventElapsedTime(&c, ctx->ev_t[4 * g + 2], ctx->ev_t[4 * g + 3]);
+                frt += f;
                 det += a;
                 slc += c;
             }
+            ctx->timing.front_ms = frt;
+            ctx->timing.front_launches = (unsigned)G;
+            unsigned stat[8];
+            CU(cudaMemcpy(stat, ctx->d_counters.p, sizeof(stat), cudaMemcpyDeviceToHost));
+            ctx->timing.front_redone = stat[4];
+            ctx->timing.front_repairs = stat[5];
             ctx->timing.h2d_ms = 0; // overlapped: only the wall total is meaningful
             ctx->timing.d2h_ms = 0;
             ctx->timing.detect_ms = det;
@@ -575,7 +628,7 @@ int r433b_process(r433b_ctx *ctx, r433b_batch const *b)
     CU(cudaEventRecord(ctx->ev[1], st));
 
     unsigned detect_launches = 0;
-    unsigned counters[4] = {0, 0, 0, 0};
+    unsigned counters[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     for (int attempt = 0; attempt < 3; ++attempt) {
         if (int r = dev_reserve(ctx, ctx->d_pkgs, ctx->pkg_cap * sizeof(r433b_package))) return r;
         if (int r = dev_reserve(ctx, ctx->d_ppool, ctx->pool_cap * sizeof(int))) return r;
@@ -587,7 +640,7 @@ int r433b_process(r433b_ctx *ctx, r433b_batch const *b)
         dp.pool_cap = (unsigned)std::min<size_t>(ctx->pool_cap, 0xffffffffu);
         CU(cudaMemsetAsync(ctx->d_counters.p, 0, 64, st));
         if (b->n_streams) {
-            launch_detect(dp, st);
+            launch_detect(dp, st, ctx->ev[4]);
             CU(cudaGetLastError());
             detect_launches++;
         }
@@ -638,7 +691,15 @@ int r433b_process(r433b_ctx *ctx, r433b_batch const *b)
     CU(cudaEventRecord(ctx->ev[3], st));
     CU(cudaEventSynchronize(ctx->ev[3]));
     cudaEventElapsedTime(&ctx->timing.h2d_ms, ctx->ev[0], ctx->ev[1]);
-    cudaEventElapsedTime(&ctx->timing.detect_ms, ctx->ev[1], ctx->ev[2]);
+    ctx->timing.front_ms = 0;
+    if (detect_launches) {
+        cudaEventElapsedTime(&ctx->timing.front_ms, ctx->ev[1], ctx->ev[4]);
+        cudaEventElapsedTime(&ctx->timing.detect_ms, ctx->ev[4], ctx->ev[2]);
+    } else
+        cudaEventElapsedTime(&ctx->timing.detect_ms, ctx->ev[1], ctx->ev[2]);
+    ctx->timing.front_launches = detect_launches;
+    ctx->timing.front_redone = counters[4];
+    ctx->timing.front_repairs = counters[5];
     cudaEventElapsedTime(&ctx->timing.slice_ms, ctx->ev[2], ctx->ev[3]);
     cudaEventElapsedTime(&ctx->timing.total_ms, ctx->ev[0], ctx->ev[3]);
     ctx->timing.d2h_ms = 0;
@@ -726,7 +787,7 @@ int r433b_copy_stage(r433b_ctx *ctx, uint32_t stream, int16_t *am, int16_t *fm, 
     uint64_t n = ctx->lengths[stream] / SS;
     if (n > max_samples) n = max_samples;
     if (n) {
-        CU(cudaMemcpy(am, (int16_t const *)ctx->d_am.p + first, n * sizeof(int16_t), cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy(am, (int16_t const *)ctx->d_am.p + ctx->am_offsets[stream], n * sizeof(int16_t), cudaMemcpyDeviceToHost));
         CU(cudaMemcpy(fm, (int16_t const *)ctx->d_fm.p + first, n * sizeof(int16_t), cudaMemcpyDeviceToHost));
     }
     return (int)std::min<uint64_t>(n, 0x7fffffff);
@@ -848,6 +909,44 @@ int replay_stream(r433b_ctx *ctx, r433b_results const *res, uint32_t stream, Per
 } // namespace
 
 extern "C" {
+
+// Position-independent checksum of everything the batch holds for one stream: package headers (without the
+// fields that say where in the batch they lie), pulse and gap widths, and the event bytes of every
+// (package, device) pair in device order.  Two streams with the same samples give the same digest wherever
+// they sit in a batch.
+int r433b_stream_digest(r433b_ctx *ctx, r433b_results const *res, uint32_t stream, uint64_t *digest)
+{
+    if (!ctx || !res || !digest) return R433B_EINVAL;
+    if (!ctx->fetched) return fail(ctx, R433B_ESTATE, "digest before fetch");
+    uint64_t h = 1469598103934665603ull; // FNV-1a, 64 bit, over 32-bit words
+    auto mix = [&](uint32_t w) {
+        h ^= w;
+        h *= 1099511628211ull;
+    };
+    auto mix_words = [&](void const *ptr, size_t n_words) {
+        uint32_t const *w = (uint32_t const *)ptr;
+        for (size_t i = 0; i < n_words; ++i) mix(w[i]);
+    };
+    r433b_package const *begin = std::lower_bound(res->packages, res->packages + res->n_packages, stream,
+            [](r433b_package const &k, uint32_t s) { return k.stream < s; });
+    for (r433b_package const *k = begin; k != res->packages + res->n_packages && k->stream == stream; ++k) {
+        uint32_t const hdr[] = {k->seq, (uint32_t)k->type, (uint32_t)k->block, (uint32_t)k->offset, (uint32_t)(k->offset >> 32),
+                                (uint32_t)k->end_pos, (uint32_t)(k->end_pos >> 32), k->start_ago, k->end_ago, k->num_pulses,
+                                k->pulse_count, (uint32_t)k->ook_low_estimate, (uint32_t)k->ook_high_estimate,
+                                (uint32_t)k->fsk_f1_est, (uint32_t)k->fsk_f2_est};
+        mix_words(hdr, sizeof(hdr) / 4);
+        mix_words(res->pulse_pool + k->pulse_off, k->pulse_count);
+        mix_words(res->gap_pool + k->pulse_off, k->pulse_count);
+        for (uint32_t dv = 0; dv < res->n_devices; ++dv) {
+            r433b_pair const &pr = res->pairs[(size_t)k->first_pair + dv];
+            mix(pr.bytes);
+            mix(pr.events);
+            if (pr.bytes) mix_words(res->events + pr.offset, pr.bytes / 4);
+        }
+    }
+    *digest = h;
+    return R433B_OK;
+}
 
 int r433b_dispatch(r433b_ctx *ctx, r433b_results const *res, uint32_t stream, r433b_event_fn fn, void *user)
 {

@@ -1,18 +1,14 @@
 // r433b_detect.cuh -- k_detect: IQ -> packages, one WARP per capture stream (sm_100a).
 //
-// The warp walks its stream in tiles of 2048 samples.  Per tile:
+// The AM (envelope + low-pass) of every sample was made by k_front (r433b_front.cuh), tile-parallel, and lies
+// in HBM as 16 bits per sample with the bounds of every 64-sample chunk.  The warp walks its stream in tiles
+// of 2048 samples.  Per tile:
 //
-//  1. AM front, lane-parallel and exact.  Lane l owns the 64 consecutive samples [64 l, 64 l + 64) of the
-//     tile (one 128-byte line of cu8 IQ).  The envelope low-pass y' = (a y + b (x + x')) >> 14
-//     (src/baseband.c:145-169) is a floor map, not associative -- but it contracts by a / 2^14 = 0.854 per
-//     sample, so a trajectory started from ANY state is, after a few dozen samples of live signal, the true
-//     one.  Every lane therefore starts kWarmAm samples in front of its chunk from a guess (the local
-//     envelope), runs ONE trajectory through warm-up and chunk, and the warp then VERIFIES: lane l's state
-//     at its chunk boundary must equal lane l-1's state at its chunk end.  Lane 0 starts from the carried
-//     exact state, so by induction a clean check proves every lane exact.  A lane that fails (about one
-//     chunk in a thousand) redoes its chunk from the now-known exact start.  No monotonicity is needed,
-//     constant input only makes the redo chain longer.  One envelope needs 2.5 instructions (xor + 2 and +
-//     2 dp4a per pair of samples), one filter step 4; AM goes to shared memory as 16 bits per sample.
+//  1. Hand-over check.  k_front started every tile but the first of a stream from a GUESS of the filter state.
+//     The filter state is its own last output, so the tile fits its predecessor iff
+//     step(last AM of the previous tile, x[-1], x[0]) equals the first stored AM of this one.  If not (rare),
+//     the walk recomputes forward from the exact state until its values meet the stored ones again; from
+//     there on the stored values are the exact ones (k_front's chunks are consistent with each other).
 //
 //  2. The package detector (src/pulse_detect.c:199-483) walks the tile warp-uniformly with ballot scans for
 //     the states whose thresholds are frozen (IDLE stretches by bracket rounds, GAP, GAP_START) and a
@@ -34,22 +30,14 @@
 //         evaluation goes further back, in the end over the whole log from the exactly known value after
 //         the first pulse.  A full log is folded into that value the same way.
 //
-// IQ is read once from HBM (plus L1/L2 hits for the warm-up overlap and the FM windows); no intermediate
-// ever leaves the SM.
+// HBM traffic per sample: IQ once and AM once in k_front, AM once here (plus the IQ of the FM windows).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
 
 #include "../../include/r433b.h"
 #include "r433b_core.cuh"
-
-#ifdef R433B_SIMT_EMU
-#define R4_DYN_SMEM(type, name) type *name = reinterpret_cast<type *>(simt::st().dyn_smem)
-#define R4_NOINLINE
-#else
-#define R4_DYN_SMEM(type, name) extern __shared__ __align__(16) type name[]
-#define R4_NOINLINE __noinline__
-#endif
+#include "r433b_front.cuh"
 
 #ifndef R4_NO_PULSE0
 #define R4_NO_PULSE0 0
@@ -60,11 +48,8 @@ constexpr int kTrainInts = 4 * kMaxPulses; // per-stream scratch: ook pulse/gap,
 constexpr int kDetectWarps = 4;            // warps (streams) per CTA
 constexpr int kDetectCtasPerSm = 7;        // 28 warps per SM: 4096 streams are co-resident on 148 SMs
 
-constexpr int kChunk = 64;                 // samples per lane per tile
-constexpr int kTile = 32 * kChunk;         // 2048
 constexpr int kAmStride = kChunk / 2 + 1;  // words between lane chunks of the 16-bit AM tile (odd: conflict-free)
 constexpr int kAmWords = 32 * kAmStride;
-constexpr int kWarmAm = 64;                // warm-up samples of the AM trajectory (multiple of 16, <= kChunk)
 constexpr int kFmWin = 256;                // FM window
 constexpr int kFmSub = kFmWin / 32;        // samples per lane of a window
 constexpr int kFmPadded = kFmWin + kFmWin / kFmSub; // padded index space: i + i / kFmSub
@@ -94,7 +79,7 @@ struct alignas(16) WarpSmem {
 // Everything one stream carries from one launch to the next when a batch is processed in time slices.
 struct StreamState {
     DetState d;
-    int y_am, x_prev;
+    int y_am;
     unsigned long long fm_pos;
     int fm_y, fm_xf;
     unsigned log_n, last_start, last_count;
@@ -106,6 +91,7 @@ struct DetectParams {
     uint8_t const *data;
     unsigned long long const *offsets; // bytes, n_streams + 1
     unsigned long long const *lengths; // optional: bytes of stream i actually used
+    unsigned long long const *am_offsets; // first sample of stream i in `am` (k_front's output)
     unsigned n_streams;
     unsigned stream0, stream_end;      // the streams this launch covers
     unsigned long long sample_begin, sample_end; // the slice of every stream this launch covers (multiples of the tile)
@@ -113,6 +99,7 @@ struct DetectParams {
     struct StreamState *state;         // per-stream carried state between launches of one batch
     int use_mag, enable_fm, fpdm;
     int lazy_fm;   // make FM windows on demand (needs the monotone FM filter: wrap_free)
+    int want_stages; // the FM stage array is wanted for every sample (fm_out)
     unsigned flip; // XOR mask applied to every loaded word: 0x80808080 turns cs8 into cu8
     unsigned rate, block_samples;
     Levels lv;
@@ -125,7 +112,9 @@ struct DetectParams {
     int *pulse_pool, *gap_pool;
     unsigned pool_cap;
     unsigned *counters; // [0] packages, [1] pool entries, [2] overflow flag, [4..] statistics
-    int16_t *am_out, *fm_out; // optional stage dump, indexed by offsets[s]/SS + n
+    int16_t *am;               // k_front's output (repaired in place where a tile did not fit its predecessor)
+    ChunkInfo const *chunks;   // bounds of every 64-sample chunk of `am`
+    int16_t *fm_out;           // optional stage dump, indexed by offsets[s]/SS + n
 };
 
 struct WarpCtx {
@@ -133,81 +122,6 @@ struct WarpCtx {
     int nlanes;
     __device__ __forceinline__ void sync() { __syncwarp(); }
 };
-
-template <int SS>
-struct Fmt {
-    static constexpr int SPL = 16 / SS; // samples per 128-bit load
-};
-
-// 16 contiguous bytes (8 cu8 / 4 cs16 samples) starting at sample `pos` of the stream: one 128-bit load;
-// zero-filled past `n_valid` samples counted from pos.
-template <int SS>
-__device__ __forceinline__ void load_group(uint8_t const *src, unsigned long long pos, long long n_valid, unsigned flip,
-        uint32_t (&rw)[4])
-{
-    constexpr int SPL = 16 / SS;
-    uint8_t const *g = src + pos * SS;
-    if (n_valid >= SPL) {
-        uint4 v = __ldg(reinterpret_cast<uint4 const *>(g));
-        rw[0] = v.x ^ flip;
-        rw[1] = v.y ^ flip;
-        rw[2] = v.z ^ flip;
-        rw[3] = v.w ^ flip;
-    } else {
-        rw[0] = rw[1] = rw[2] = rw[3] = 0u;
-        int nb = n_valid > 0 ? (int)n_valid * SS : 0;
-        for (int bidx = 0; bidx < nb; ++bidx) rw[bidx >> 2] |= (uint32_t)(g[bidx] ^ (flip & 0xff)) << (8 * (bidx & 3));
-    }
-}
-
-// -Y magest on cu8 (src/baseband.c:65-79): rarely asked for, kept out of the hot loops' instruction stream
-// (two magnitudes per returned word: they are below 2^15)
-__device__ R4_NOINLINE uint4 mag_group_cu8(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3)
-{
-    auto two = [](uint32_t w) {
-        return (uint32_t)mag_cu8((int)(w & 0xff), (int)((w >> 8) & 0xff))
-                | ((uint32_t)mag_cu8((int)((w >> 16) & 0xff), (int)(w >> 24)) << 16);
-    };
-    uint4 r;
-    r.x = two(w0);
-    r.y = two(w1);
-    r.z = two(w2);
-    r.w = two(w3);
-    return r;
-}
-
-// envelope / magnitude of the SPL samples of one group (src/baseband.c:36-45, :65-79, :96-110)
-template <int SS>
-__device__ __forceinline__ void env_group(uint32_t const (&rw)[4], int use_mag, int (&x)[16 / SS])
-{
-    if (SS == 2) {
-        if (!use_mag) {
-            // (127 - I)^2 + (127 - Q)^2: 127 - v is v ^ 0x7f read as a signed byte; one dp4a squares and adds a pair
-#pragma unroll
-            for (int w = 0; w < 4; ++w) {
-                uint32_t s = rw[w] ^ 0x7f7f7f7fu;
-                x[2 * w] = __dp4a((int)s, (int)(s & 0x0000ffffu), 0);
-                x[2 * w + 1] = __dp4a((int)s, (int)(s & 0xffff0000u), 0);
-            }
-        } else {
-            uint4 const m = mag_group_cu8(rw[0], rw[1], rw[2], rw[3]);
-            x[0] = (int)(m.x & 0xffff);
-            x[1] = (int)(m.x >> 16);
-            x[2] = (int)(m.y & 0xffff);
-            x[3] = (int)(m.y >> 16);
-            x[4] = (int)(m.z & 0xffff);
-            x[5] = (int)(m.z >> 16);
-            x[6] = (int)(m.w & 0xffff);
-            x[7] = (int)(m.w >> 16);
-        }
-    } else {
-#pragma unroll
-        for (int j = 0; j < 16 / SS; ++j) {
-            uint32_t w = rw[j & 3];
-            x[j] = mag_cs16((int)(int16_t)(w & 0xffff), (int)(int16_t)(w >> 16));
-        }
-    }
-}
 
 __device__ __forceinline__ int fm_pidx(int i) { return i + i / kFmSub; }
 
@@ -583,6 +497,36 @@ __device__ R4_NOINLINE int f1_evaluate(FmJob<SS> const &jb, WarpSmem &sm, unsign
     }
 }
 
+// ------------------------------------------------------------------ tile hand-over repair ---
+
+// The tile at t0 does not continue the exact filter state `y` (the last AM value in front of it; xp = x[-1] as
+// the filter sees it): recompute forward until the values meet the stored ones.  Every lane runs the same
+// (warp-uniform) recurrence; lane 0 patches the shared-memory tile, the copy in HBM and the chunk bounds.
+template <int SS>
+__device__ R4_NOINLINE void am_repair(WarpSmem &sm, uint8_t const *src, unsigned long long t0, int nv_tile, int y, int xp,
+        int a1, int b0, unsigned flip, int use_mag, int16_t *am_tile)
+{
+    int const lane = threadIdx.x & 31;
+    uint16_t *am16 = reinterpret_cast<uint16_t *>(sm.am);
+    for (int n = 0; n < nv_tile; ++n) {
+        int const x = env_at<SS>(src, t0 + (unsigned long long)n, flip, use_mag);
+        y = iir16_nowrap(y, a1, b0, x + xp);
+        xp = x;
+        int const idx = (n >> 6) * (2 * kAmStride) + (n & 63);
+        if (y == (int)(int16_t)am16[idx]) break;
+        __syncwarp();
+        if (lane == 0) {
+            am16[idx] = (uint16_t)y;
+            am_tile[n] = (int16_t)y;
+            int const c = n >> 6;
+            if (y < sm.cmin[c]) sm.cmin[c] = y;
+            if (y > sm.cmax[c]) sm.cmax[c] = y;
+        }
+        __syncwarp();
+    }
+    __syncwarp();
+}
+
 // --------------------------------------------------------------------------- kernel ------
 
 template <int SS>
@@ -605,6 +549,8 @@ __global__ void __launch_bounds__(kDetectWarps * 32, kDetectCtasPerSm) k_detect(
     unsigned long long const byte0 = p.offsets[s];
     unsigned long long const N = (p.lengths ? p.lengths[s] : p.offsets[s + 1] - byte0) / SS;
     uint8_t const *const src = p.data + byte0;
+    int16_t *const am_stream = p.am + p.am_offsets[s];
+    ChunkInfo const *const chunk_stream = p.chunks + p.am_offsets[s] / kChunk;
 
     Trains tr;
     tr.ook_pulse = p.train_scratch + (size_t)s * kTrainInts;
@@ -628,14 +574,14 @@ __global__ void __launch_bounds__(kDetectWarps * 32, kDetectCtasPerSm) k_detect(
     jb.monotone = p.wrap_free;
     jb.fm_out = p.fm_out ? p.fm_out + byte0 / SS : nullptr;
     // FM windows on demand need the rigorous state rebuild (monotone filter); the stage dump wants every sample
-    bool const lazy_fm = !fm_on || (p.wrap_free && p.lazy_fm && !p.am_out);
+    bool const lazy_fm = !fm_on || (p.wrap_free && p.lazy_fm && !p.want_stages);
     // the deferred carrier estimate re-makes FM for logged samples later: needs the state rebuild as well
     bool const defer_f1 = !fm_on || p.wrap_free != 0;
 
     DetState d;
     unsigned seq = 0;
     int const per_ms = (int)(p.rate / 1000);
-    int y_am = 0, x_prev = 0; // carried AM filter state (reset_sdr_flow(): zero)
+    int y_am = 0; // the last AM value of the previous tile: the AM filter state (reset_sdr_flow(): zero)
     int flushed = 0;
     unsigned log_n = 0, log_start = 0, log_count = 0; // deferred carrier-estimate log: closed entries, the open entry
     if (p.first_chunk) {
@@ -649,7 +595,6 @@ __global__ void __launch_bounds__(kDetectWarps * 32, kDetectCtasPerSm) k_detect(
         StreamState const &ss = p.state[s];
         d = ss.d;
         y_am = ss.y_am;
-        x_prev = ss.x_prev;
         seq = ss.seq;
         flushed = ss.flushed;
         if (lane == 0) {
@@ -766,120 +711,44 @@ __global__ void __launch_bounds__(kDetectWarps * 32, kDetectCtasPerSm) k_detect(
         unsigned long long const remain = N - t0;
         int const nv_tile = remain < (unsigned long long)T ? (int)remain : T;
 
-        // ---- AM front ---------------------------------------------------------------------------
-        // The (warp-uniform) detector state is not needed here: park it so the loops have the registers.
-        if (lane == 0) sm.park = d;
-        __syncwarp();
+        // ---- AM tile from HBM ---------------------------------------------------------------------
         {
-            int const base = lane * C;
-            int nv = nv_tile - base;
-            nv = nv < 0 ? 0 : (nv > C ? C : nv);
+            uint4 const *g = reinterpret_cast<uint4 const *>(am_stream + t0 + (unsigned long long)(lane * C));
             uint32_t *const mine = sm.am + lane * kAmStride;
-            unsigned long long const gpos = t0 + (unsigned long long)base; // first sample of the chunk in the stream
-            // the reference keeps x[-1] as int16 across block calls (src/baseband.c:167)
-            int const x_carry = (t0 % p.block_samples == 0) ? (int)(int16_t)x_prev : x_prev;
-            int y, xp;
-            bool const exact = lane == 0;
-            if (exact) {
-                y = y_am;
-                xp = x_carry;
-            } else if (nv > 0) {
-                // guess: the filter has (almost) unit gain, its state is near the local envelope
-                uint32_t rw[4];
-                int x[SPL];
-                if (gpos >= (unsigned long long)(kWarmAm + SPL)) {
-                    load_group<SS>(src, gpos - kWarmAm - SPL, SPL, p.flip, rw);
-                    env_group<SS>(rw, p.use_mag, x);
-                    xp = x[SPL - 1];
-                    y = (x[SPL - 1] + x[SPL - 2]) >> 1;
-                    if (y > 32767) y = 32767;
-                } else { // the warm-up begins at sample 0 of the stream (gpos == kWarmAm): the reset state, exact
-                    xp = 0;
-                    y = 0;
-                }
-#pragma unroll 1
-                for (int g = -kWarmAm; g < 0; g += SPL) {
-                    load_group<SS>(src, gpos + g, SPL, p.flip, rw);
-                    env_group<SS>(rw, p.use_mag, x);
+            uint4 v[4];
 #pragma unroll
-                    for (int j = 0; j < SPL; ++j) {
-                        y = iir16_nowrap(y, a1, b0, x[j] + xp);
-                        xp = x[j];
-                    }
-                }
-            } else {
-                y = 0;
-                xp = 0;
-            }
-            int const y_b = y, xp_b = xp;
-            int y_end = y, xp_end = xp, cmin = 32767, cmax = 0;
-            int16_t *const am_dump = p.am_out ? p.am_out + byte0 / SS + gpos : nullptr;
-            // verify / redo loop: a lane's state at its chunk boundary must be what its left neighbour ended
-            // with (lane 0 starts from the carried exact state); the lowest lane that fails runs its chunk
-            // again from that exact state.  cmin / cmax only ever widen: they stay bounds.
-            int ys = y_b;
-            bool run = true, fixed = false;
-            for (;;) {
-                if (run) {
-                    int yy = ys, xx = xp_b;
-                    int k = 0;
-#pragma unroll 1
-                    for (; k + SPL <= nv; k += SPL) {
-                        uint32_t rw[4];
-                        int x[SPL];
-                        load_group<SS>(src, gpos + k, SPL, p.flip, rw);
-                        env_group<SS>(rw, p.use_mag, x);
+            for (int h = 0; h < 2; ++h) {
 #pragma unroll
-                        for (int j = 0; j < SPL; j += 2) {
-                            int ya = iir16_nowrap(yy, a1, b0, x[j] + xx);
-                            int yb = iir16_nowrap(ya, a1, b0, x[j + 1] + x[j]);
-                            xx = x[j + 1];
-                            yy = yb;
-                            cmin = min(cmin, min(ya, yb));
-                            cmax = max(cmax, max(ya, yb));
-                            mine[(k + j) >> 1] = (uint32_t)ya | ((uint32_t)yb << 16);
-                            if (am_dump) {
-                                am_dump[k + j] = (int16_t)ya;
-                                am_dump[k + j + 1] = (int16_t)yb;
-                            }
-                        }
-                    }
-                    if (k < nv) { // ragged end of the stream
-                        uint32_t rw[4];
-                        int x[SPL];
-                        load_group<SS>(src, gpos + k, nv - k, p.flip, rw);
-                        env_group<SS>(rw, p.use_mag, x);
-                        uint16_t *m16 = reinterpret_cast<uint16_t *>(mine);
-                        for (int j = 0; k + j < nv; ++j) {
-                            yy = iir16_nowrap(yy, a1, b0, x[j] + xx);
-                            xx = x[j];
-                            cmin = min(cmin, yy);
-                            cmax = max(cmax, yy);
-                            m16[k + j] = (uint16_t)yy;
-                            if (am_dump) am_dump[k + j] = (int16_t)yy;
-                        }
-                    }
-                    y_end = yy;
-                    xp_end = xx;
-                }
-                int prev_end = __shfl_up_sync(0xffffffffu, y_end, 1);
-                bool ok = exact || fixed || nv == 0 || y_b == prev_end;
-                unsigned bad = __ballot_sync(0xffffffffu, !ok);
-                if (!bad) break;
-                int const f = __ffs(bad) - 1; // lanes below f are exact
-                ys = __shfl_sync(0xffffffffu, y_end, f - 1);
-                run = lane == f;
-                if (run) {
-                    fixed = true;
-                    atomicAdd(&p.counters[4], 1u);
+                for (int i = 0; i < 4; ++i) v[i] = g[4 * h + i];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    mine[16 * h + 4 * i + 0] = v[i].x;
+                    mine[16 * h + 4 * i + 1] = v[i].y;
+                    mine[16 * h + 4 * i + 2] = v[i].z;
+                    mine[16 * h + 4 * i + 3] = v[i].w;
                 }
             }
-            sm.cmin[lane] = nv > 0 ? cmin : 32767;
-            sm.cmax[lane] = nv > 0 ? cmax : 0;
-            int const last_lane = (nv_tile - 1) / C;
-            y_am = __shfl_sync(0xffffffffu, y_end, last_lane);
-            x_prev = __shfl_sync(0xffffffffu, xp_end, last_lane);
+            ChunkInfo const ci = chunk_stream[t0 / C + lane];
+            bool const has = lane * C < nv_tile;
+            sm.cmin[lane] = has ? (int)ci.cmin : 32767;
+            sm.cmax[lane] = has ? (int)ci.cmax : 0;
         }
+        __syncwarp();
+        // hand-over check (see the file header): the first tile of a stream starts from the reset state in k_front
+        if (t0 != 0) {
+            int const x0 = env_at<SS>(src, t0, p.flip, p.use_mag);
+            int xm = env_at<SS>(src, t0 - 1, p.flip, p.use_mag);
+            // the reference keeps x[-1] as int16 across block calls (src/baseband.c:167)
+            if (t0 % p.block_samples == 0) xm = (int)(int16_t)xm;
+            int const expect = iir16_nowrap(y_am, a1, b0, x0 + xm);
+            if (expect != (int)(int16_t)am16[0]) {
+                am_repair<SS>(sm, src, t0, nv_tile, y_am, xm, a1, b0, p.flip, p.use_mag, am_stream + t0);
+                if (lane == 0) atomicAdd(&p.counters[5], 1u);
+            }
+        }
+        y_am = (int)(int16_t)am16[((nv_tile - 1) >> 6) * (2 * kAmStride) + ((nv_tile - 1) & 63)];
+        // The (warp-uniform) detector state is not needed by the FM tile pass: park it so its loops have the registers.
+        if (lane == 0) sm.park = d;
         __syncwarp();
         // ---- FM for the whole tile when it cannot be made on demand -----------------------------
         if (!lazy_fm || (!fm_on && p.fm_out)) {
@@ -1282,7 +1151,6 @@ __global__ void __launch_bounds__(kDetectWarps * 32, kDetectCtasPerSm) k_detect(
         StreamState &ss = p.state[s];
         ss.d = d;
         ss.y_am = y_am;
-        ss.x_prev = x_prev;
         ss.fm_pos = sm.fm_pos;
         ss.fm_y = sm.fm_y;
         ss.fm_xf = sm.fm_xf;

@@ -25,7 +25,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
 EXPORTS = ["r433b_create", "r433b_destroy", "r433b_last_error", "r433b_set_levels", "r433b_set_fm_low_pass",
            "r433b_set_devices", "r433b_set_r_devices", "r433b_set_pipeline", "r433b_process", "r433b_fetch", "r433b_get_timing",
            "r433b_get_counts", "r433b_copy_stage", "r433b_event_to_bitbuffer", "r433b_package_to_pulse_data",
-           "r433b_package_file_pos", "r433b_dispatch", "r433b_dispatch_r_devices"]
+           "r433b_package_file_pos", "r433b_dispatch", "r433b_dispatch_r_devices", "r433b_stream_digest"]
 
 
 def build(force=False, verbose=False):
@@ -79,7 +79,9 @@ class Results(C.Structure):
 
 class Timing(C.Structure):
     _fields_ = [("h2d_ms", C.c_float), ("detect_ms", C.c_float), ("slice_ms", C.c_float), ("d2h_ms", C.c_float),
-                ("total_ms", C.c_float), ("detect_launches", C.c_uint32), ("slice_launches", C.c_uint32)]
+                ("total_ms", C.c_float), ("detect_launches", C.c_uint32), ("slice_launches", C.c_uint32),
+                ("front_ms", C.c_float), ("front_launches", C.c_uint32), ("front_redone", C.c_uint32),
+                ("front_repairs", C.c_uint32)]
 
 
 class PulseData(C.Structure):
@@ -123,6 +125,7 @@ def load():
     L.r433b_fetch.argtypes = [C.c_void_p, C.POINTER(Results)]
     L.r433b_get_timing.argtypes = [C.c_void_p, C.POINTER(Timing)]
     L.r433b_get_counts.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
+    L.r433b_stream_digest.argtypes = [C.c_void_p, C.POINTER(Results), C.c_uint32, C.POINTER(C.c_uint64)]
     L.r433b_copy_stage.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint64]
     L.r433b_event_to_bitbuffer.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.POINTER(C.c_uint32)]
     L.r433b_package_to_pulse_data.argtypes = [C.c_void_p, C.POINTER(Results), C.c_uint32, C.POINTER(PulseData)]
@@ -230,6 +233,12 @@ class Context:
                 "pairs": view(r.pairs, npk * r.n_devices * 16, PAIR_DTYPE).reshape(npk, r.n_devices) if npk and r.n_devices else np.zeros((0, 0), PAIR_DTYPE),
                 "events": view(r.events, r.event_bytes, np.uint8), "event_bytes": r.event_bytes, "n_events": r.n_events,
                 "n_samples": r.n_samples}
+
+    def stream_digest(self, stream):
+        """Position-independent checksum of everything the fetched batch holds for one stream."""
+        out = C.c_uint64(0)
+        self._check(self.L.r433b_stream_digest(self.h, C.byref(self._res), stream, C.byref(out)))
+        return out.value
 
     def copy_stage(self, stream, n):
         am = np.zeros(n, np.int16)

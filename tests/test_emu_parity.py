@@ -27,7 +27,8 @@ from test_gpu_parity import (ctx, devices,  # noqa: E402,F401  (fixtures)
                              test_against_compiled_reference, test_all_protocols_including_disabled,
                              test_cs8_input_is_cu8_plus_128, test_custom_piwm_raw_and_nrzs_devices,
                              test_fm_low_pass_override_and_wrapping_filter, test_fm_rebuild_after_constant_input,
-                             test_fsk_cs16_minmax_and_classic, test_fsk_train_overflow_shifts_the_pulse_train,
+                             test_front_guesses_verified_and_repaired, test_fsk_cs16_minmax_and_classic,
+                             test_fsk_train_overflow_shifts_the_pulse_train,
                              test_magnitude_mode_and_fixed_level, test_ook_1200_pulse_end_of_package,
                              test_ook_cu8_default_devices, test_pipelined_time_slices_identical,
                              test_priority_classes_stop_after_a_decode, test_ragged_lengths_and_small_blocks,

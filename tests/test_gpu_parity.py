@@ -362,3 +362,27 @@ def test_rates_and_formats_round_1_never_compared(ctx, devices):
         ref = o.run(streams[0], 2, 250000, freq)
         assert any(p["type"] == 2 for p in ref["packages"])
         check(gpu[0], ref, f"cu8 FSK {freq}")
+
+
+def test_front_guesses_verified_and_repaired(devices, monkeypatch):
+    """k_front starts every chunk from a GUESS of the AM filter state; a wrong guess must be caught -- inside a
+    tile by the warp's verify / redo chain, at a tile start by k_detect's hand-over check and repair.
+    R433B_SPOIL_FRONT makes the guesses wrong on purpose (1: the first chunk of every tile, 2: every chunk):
+    stage arrays, packages and events must not change, and the counters must show that the paths ran."""
+    streams = [synth.ook_stream(61, n_samples=1 << 17, n_bursts=2), synth.ook_stream(62, n_samples=(1 << 17) - 16 * 37, n_bursts=2)]
+    o = oracle_for(devices)
+    refs = [o.run(s, 2) for s in streams]
+    for spoil in (1, 2):
+        monkeypatch.setenv("R433B_SPOIL_FRONT", str(spoil))
+        c = lib.Context(0)
+        monkeypatch.delenv("R433B_SPOIL_FRONT")
+        c.set_devices(devices)
+        gpu = run_gpu(c, streams, lib.FMT_CU8, 250000, 433920000)
+        tm = c.timing()
+        c.close()
+        for i in range(len(streams)):
+            check(gpu[i], refs[i], f"spoil {spoil} stream {i}")
+        tiles = sum((len(s) // 2 + 2047) // 2048 for s in streams)
+        assert tm["front_repairs"] >= tiles - len(streams) - 2, tm
+        if spoil == 2:
+            assert tm["front_redone"] >= 20 * tiles, tm

@@ -9,6 +9,8 @@ import io
 import os
 import subprocess
 import sys
+import os as _os
+KF = ["-k", "regex:" + _os.environ["NCU_KERNEL"]] if _os.environ.get("NCU_KERNEL") else []
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 rep, which = sys.argv[1], sys.argv[2]
@@ -20,8 +22,8 @@ MARKS = {
         ("fm: state rebuild (fm_cold)", "void fm_cold("), ("fm: window low-pass (fm_window)", "void fm_window("),
         ("fm: demand", "void fm_demand("), ("deferred carrier estimate (f1_evaluate)", "int f1_step("),
         ("prologue", "k_detect(DetectParams p)"), ("log_append", "auto log_append = [&]"), ("emit", "auto emit = [&]"),
-        ("tile loop top / AM warm-up", "for (unsigned long long t0 = p.sample_begin"),
-        ("AM chunk pass + verify", "// verify / redo loop: a lane's state at its chunk boundary"),
+        ("am_repair", "void am_repair("),
+        ("tile loop top / AM tile load + hand-over check", "for (unsigned long long t0 = p.sample_begin"),
         ("tile FM pass / fm_need", "// ---- FM for the whole tile when it cannot be made on demand"),
         ("idle_tile", "auto idle_tile = [&]"), ("idle_fast", "auto idle_fast = [&]"), ("gap_fast", "auto gap_fast = [&]"),
         ("pulse_fast", "auto pulse_fast = [&]"), ("pulse0_fast (first pulse + FSK)", "auto pulse0_fast = [&]"),
@@ -41,7 +43,7 @@ for name, needle in marks:
             break
 pos.sort()
 
-out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--print-source", "cuda,sass", "--csv"], capture_output=True, text=True).stdout
+out = subprocess.run(["ncu", "-i", rep] + KF + [ "--page", "source", "--print-source", "cuda,sass", "--csv"], capture_output=True, text=True).stdout
 cur, hd = None, None
 reg = collections.defaultdict(lambda: [0.0, 0.0, 0.0, 0])
 last_region = None

@@ -6,10 +6,12 @@ import io
 import json
 import subprocess
 import sys
+import os as _os
+KF = ["-k", "regex:" + _os.environ["NCU_KERNEL"]] if _os.environ.get("NCU_KERNEL") else []
 
 rep, out_md = sys.argv[1], sys.argv[2]
 traffic_json = sys.argv[3] if len(sys.argv) > 3 else None
-raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+raw = subprocess.run(["ncu", "-i", rep] + KF + [ "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
 hdr, units, vals = rows[0], rows[1], rows[2]
 m = {h: (v, u) for h, u, v in zip(hdr, units, vals)}
@@ -46,7 +48,7 @@ if traffic_json:
     json.dump({"kernel": kernel, "dram_bytes_per_launch": int(rd + wr), "dram_bytes_read": int(rd), "dram_bytes_write": int(wr),
                "workload": "4096 x 2^20-sample cu8 streams (tools/quick_perf.py --streams 4096 --distinct 32)", "report": rep},
               open(traffic_json, "w"), indent=1)
-src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--print-source", "cuda,sass", "--csv"], capture_output=True, text=True).stdout
+src = subprocess.run(["ncu", "-i", rep] + KF + [ "--page", "source", "--print-source", "cuda,sass", "--csv"], capture_output=True, text=True).stdout
 cur, hd, agg = None, None, collections.OrderedDict()
 for r in csv.reader(io.StringIO(src)):
     if not r:
