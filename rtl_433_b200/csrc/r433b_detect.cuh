@@ -58,6 +58,44 @@ constexpr int kFmWindowsPerTile = kTile / kFmWin;
 constexpr unsigned kLogCap = 1024;         // deferred carrier-estimate log: entries per stream
 constexpr int kF1Tail = 1536;              // samples of the first evaluation attempt
 
+struct FmJob {
+    uint8_t const *src;        // the stream
+    unsigned long long N;      // its length in samples
+    unsigned flip;
+    long long a1, b0;
+    int fm_on;                 // 0: "FM" is the raw envelope (buf.fm aliases buf.temp when nothing asks for FM)
+    int use_mag;
+    int monotone;              // the state rebuild by range collapse is valid
+    int16_t *fm_out;           // stage dump (absolute index = stream base + sample) or nullptr
+};
+
+// Warp-uniform state of the walk.  It lives in shared memory BETWEEN the phases of the walk (idle_run, burst_run,
+// generic_step, walk_emit: separate functions, each with the registers and the instruction footprint of its own
+// loop); a phase loads what it needs into registers, every lane computes the same values, lane 0 stores them back.
+struct WalkState {
+    DetState d;
+    unsigned log_n, log_start, log_count; // deferred carrier-estimate log: closed entries (global memory), the open entry
+    unsigned seq;
+    int pend_type;               // a finished package to hand over (1 OOK, 2 FSK) ...
+    unsigned long long pend_pos; // ... returned at this stream position
+    unsigned long long t0;       // the tile being walked
+    int nv_tile;
+};
+
+// Per-stream constants of the walk (written once by lane 0)
+struct WalkConst {
+    FmJob jb;
+    Trains tr;
+    unsigned *log;
+    Levels lv;
+    int per_ms, fpdm, lazy_fm, defer_f1;
+    unsigned stream, block_samples;
+    r433b_package *pkgs;
+    int *pulse_pool, *gap_pool;
+    unsigned pkg_cap, pool_cap;
+    unsigned *counters;
+};
+
 // Shared memory of one warp
 struct alignas(16) WarpSmem {
     uint32_t am[kAmWords];       // AM tile, 16 bits per sample: sample n at u16 (n / 64) * 66 + n % 64
@@ -73,7 +111,8 @@ struct alignas(16) WarpSmem {
     int tile_state_y[kFmWindowsPerTile], tile_state_xf[kFmWindowsPerTile]; // eager mode: state in front of each window
     unsigned long long tile_end_pos; // eager mode: the contiguous filter state at the end of the tile pass
     int tile_end_y, tile_end_xf;
-    DetState park;
+    WalkState ws;
+    WalkConst wc;
 };
 
 // Everything one stream carries from one launch to the next when a batch is processed in time slices.
@@ -150,23 +189,12 @@ __device__ __forceinline__ int fm_step(int y, long long a1, long long b0, int v,
     return iir32(y, a1, b0, (long long)v + vp);
 }
 
-template <int SS>
-struct FmJob {
-    uint8_t const *src;        // the stream
-    unsigned long long N;      // its length in samples
-    unsigned flip;
-    long long a1, b0;
-    int fm_on;                 // 0: "FM" is the raw envelope (buf.fm aliases buf.temp when nothing asks for FM)
-    int use_mag;
-    int monotone;              // the state rebuild by range collapse is valid
-    int16_t *fm_out;           // stage dump (absolute index = stream base + sample) or nullptr
-};
 
 // Discriminator outputs (src/baseband.c:253-262 / :346-356) of samples [a, a + n) into sm.xf[fm_pidx(i)],
 // n <= kFmWin, a a multiple of SPL; lane j of a batch takes the group at a + 32 * SPL * q + SPL * j.
 // With !fm_on the raw envelope goes straight to sm.fm instead.
 template <int SS>
-__device__ void disc_fill(FmJob<SS> const &jb, WarpSmem &sm, unsigned long long a, int n)
+__device__ void disc_fill(FmJob const &jb, WarpSmem &sm, unsigned long long a, int n)
 {
     constexpr int SPL = 16 / SS;
     int const lane = threadIdx.x & 31;
@@ -229,7 +257,7 @@ __device__ void disc_fill(FmJob<SS> const &jb, WarpSmem &sm, unsigned long long 
 // is independent of everything earlier.  K grows until they meet or the walk starts at a known state
 // (the stream start, or sm.fm_pos).  Monotone filters only.  Leaves the state in sm.fm_pos / fm_y / fm_xf.
 template <int SS>
-__device__ R4_NOINLINE void fm_cold(FmJob<SS> const &jb, WarpSmem &sm, unsigned long long pos)
+__device__ R4_NOINLINE void fm_cold(FmJob const &jb, WarpSmem &sm, unsigned long long pos)
 {
     constexpr int SPL = 16 / SS;
     int const lane = threadIdx.x & 31;
@@ -287,7 +315,7 @@ __device__ R4_NOINLINE void fm_cold(FmJob<SS> const &jb, WarpSmem &sm, unsigned 
 // FM of the window [w0, w0 + n) (n <= kFmWin, w0 a multiple of SPL) from the exact state in sm.fm_* which
 // must be the one in front of w0.  Advances sm.fm_pos to w0 + n.
 template <int SS>
-__device__ R4_NOINLINE void fm_window(FmJob<SS> const &jb, WarpSmem &sm, unsigned long long w0, int n)
+__device__ R4_NOINLINE void fm_window(FmJob const &jb, WarpSmem &sm, unsigned long long w0, int n)
 {
     int const lane = threadIdx.x & 31;
     disc_fill<SS>(jb, sm, w0, n);
@@ -363,7 +391,7 @@ __device__ R4_NOINLINE void fm_window(FmJob<SS> const &jb, WarpSmem &sm, unsigne
 // Make the window that holds sample `pos` current (lazy mode): continue the previous window when it ends
 // close in front, rebuild the state otherwise.
 template <int SS>
-__device__ R4_NOINLINE void fm_demand(FmJob<SS> const &jb, WarpSmem &sm, unsigned long long pos, unsigned long long limit)
+__device__ R4_NOINLINE void fm_demand(FmJob const &jb, WarpSmem &sm, unsigned long long pos, unsigned long long limit)
 {
     constexpr int SPL = 16 / SS;
     unsigned long long w0 = pos / SPL * SPL;
@@ -383,7 +411,7 @@ __device__ R4_NOINLINE void fm_demand(FmJob<SS> const &jb, WarpSmem &sm, unsigne
 // The window for the detector walk at tile [t0, t0 + nv_tile): on demand (lazy), or re-made from the start
 // states the tile pass kept (eager mode: windows are aligned, the end-of-tile state is put back afterwards).
 template <int SS>
-__device__ R4_NOINLINE void fm_for_walk(FmJob<SS> const &jb, WarpSmem &sm, unsigned long long pos, unsigned long long t0,
+__device__ R4_NOINLINE void fm_for_walk(FmJob const &jb, WarpSmem &sm, unsigned long long pos, unsigned long long t0,
         int nv_tile, bool lazy)
 {
     int const lane = threadIdx.x & 31;
@@ -398,7 +426,7 @@ __device__ R4_NOINLINE void fm_for_walk(FmJob<SS> const &jb, WarpSmem &sm, unsig
         sm.fm_pos = t0 + (unsigned long long)w * kFmWin;
     }
     __syncwarp();
-    FmJob<SS> quiet = jb;
+    FmJob quiet = jb;
     quiet.fm_out = nullptr;
     int const cnt = nv_tile - w * kFmWin < kFmWin ? nv_tile - w * kFmWin : kFmWin;
     fm_window<SS>(quiet, sm, t0 + (unsigned long long)w * kFmWin, cnt);
@@ -419,7 +447,7 @@ __device__ __forceinline__ int f1_step(int g, int f) { return g + f / 64 - g / 6
 // first logged sample; the log (entries = runs of consecutive updating samples, relative to the package
 // start) is in global memory except for the newest entry.  Returns the exact estimate after the last one.
 template <int SS>
-__device__ R4_NOINLINE int f1_evaluate(FmJob<SS> const &jb, WarpSmem &sm, unsigned const *log, unsigned long long start_abs,
+__device__ R4_NOINLINE int f1_evaluate(FmJob const &jb, WarpSmem &sm, unsigned const *log, unsigned long long start_abs,
         int g_base, unsigned n_closed, unsigned open_start, unsigned open_count)
 {
     int const lane = threadIdx.x & 31;
@@ -527,12 +555,616 @@ __device__ R4_NOINLINE void am_repair(WarpSmem &sm, uint8_t const *src, unsigned
     __syncwarp();
 }
 
+// ------------------------------------------------------------- the walk: phases -----------
+
+// The open entry of the deferred carrier-estimate log in registers (warp-uniform); closed entries go to the
+// stream's log in global memory.  Entries are runs of consecutive updating samples, relative to the package start.
+struct LogRegs {
+    unsigned n, start, count;
+};
+// false: the log is full and has to be folded first (nothing changed)
+__device__ __forceinline__ bool log_add(LogRegs &L, unsigned *log, unsigned rel, unsigned cnt, int lane)
+{
+    if (L.count && L.start + L.count == rel) {
+        L.count += cnt;
+        return true;
+    }
+    if (L.count) { // close the open entry
+        if (L.n == kLogCap) return false;
+        if (lane == 0) {
+            log[2 * L.n] = L.start;
+            log[2 * L.n + 1] = L.count;
+        }
+        L.n += 1;
+    }
+    L.start = rel;
+    L.count = cnt;
+    return true;
+}
+
+// eager FM mode: put the contiguous end-of-tile filter state back after windows were (re-)made out of order
+__device__ __forceinline__ void restore_tile_end(WarpSmem &sm)
+{
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0 && !sm.wc.lazy_fm) {
+        sm.fm_pos = sm.tile_end_pos;
+        sm.fm_y = sm.tile_end_y;
+        sm.fm_xf = sm.tile_end_xf;
+    }
+    __syncwarp();
+}
+
+// everything logged so far into the exact value ws.d.ook_f1 (state in shared memory)
+template <int SS>
+__device__ R4_NOINLINE void walk_f1_fold(WarpSmem &sm)
+{
+    __syncwarp();
+    int const g = f1_evaluate<SS>(sm.wc.jb, sm, sm.wc.log, sm.ws.d.start_abs, sm.ws.d.ook_f1, sm.ws.log_n, sm.ws.log_start,
+            sm.ws.log_count);
+    restore_tile_end(sm);
+    if ((threadIdx.x & 31) == 0) {
+        sm.ws.d.ook_f1 = g;
+        sm.ws.log_n = 0;
+        sm.ws.log_count = 0;
+    }
+    __syncwarp();
+}
+
+// What every entry into pulse_detect_package() does before looking at samples (det_call_boundary), on the state
+// in shared memory
+__device__ __forceinline__ void walk_call_boundary(WarpSmem &sm)
+{
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) {
+        if (sm.ws.d.high < sm.wc.lv.min_high) sm.ws.d.high = sm.wc.lv.min_high;
+        sm.ws.d.eop_flag = 0;
+    }
+    __syncwarp();
+}
+
+// Hand a finished package over: header + pulse / gap widths into the arenas (state in shared memory)
+template <int SS>
+__device__ R4_NOINLINE void walk_emit(WarpSmem &sm, int type, unsigned long long pos, bool flush)
+{
+    int const lane = threadIdx.x & 31;
+    __syncwarp();
+    if (type == 1 && (sm.ws.log_n || sm.ws.log_count)) walk_f1_fold<SS>(sm); // the carrier estimate of an OOK package is read now
+    WalkConst const &wc = sm.wc;
+    DetState const d = sm.ws.d;
+    unsigned const seq = sm.ws.seq;
+    unsigned long long const N = wc.jb.N;
+    Trains const tr = wc.tr;
+    PackageHeader h = package_header(d, type);
+    unsigned cnt = h.num_pulses + 1 < (unsigned)kMaxPulses ? h.num_pulses + 1 : (unsigned)kMaxPulses;
+    unsigned idx = 0, off = 0;
+    if (lane == 0) {
+        idx = atomicAdd(&wc.counters[0], 1u);
+        off = atomicAdd(&wc.counters[1], cnt);
+    }
+    idx = __shfl_sync(0xffffffffu, idx, 0);
+    off = __shfl_sync(0xffffffffu, off, 0);
+    bool fits = idx < wc.pkg_cap && (unsigned long long)off + cnt <= wc.pool_cap;
+    if (!fits) {
+        if (lane == 0) atomicOr(&wc.counters[2], 1u);
+    } else {
+        __syncwarp();
+        int const *sp = type == 1 ? tr.ook_pulse : tr.fsk_pulse;
+        int const *sg = type == 1 ? tr.ook_gap : tr.fsk_gap;
+        for (unsigned i = lane; i < cnt; i += 32) {
+            wc.pulse_pool[off + i] = sp[i];
+            wc.gap_pool[off + i] = sg[i];
+        }
+        if (lane == 0) {
+            unsigned long long blk = flush ? (N + wc.block_samples - 1) / wc.block_samples : pos / wc.block_samples;
+            unsigned long long bstart = blk * wc.block_samples;
+            unsigned long long blen = flush ? 0 : (N - bstart < wc.block_samples ? N - bstart : wc.block_samples);
+            r433b_package k;
+            k.stream = wc.stream;
+            k.seq = seq;
+            k.type = type;
+            k.block = (int)blk;
+            k.offset = h.offset;
+            k.end_pos = pos;
+            k.start_ago = flush ? (unsigned)(N - h.start_abs) : (unsigned)(bstart + blen - h.start_abs);
+            k.end_ago = flush ? 0u : (unsigned)(blen - (pos - bstart));
+            k.num_pulses = h.num_pulses;
+            k.pulse_off = off;
+            k.pulse_count = cnt;
+            k.ook_low_estimate = h.low;
+            k.ook_high_estimate = h.high;
+            k.fsk_f1_est = h.f1;
+            k.fsk_f2_est = h.f2;
+            k.first_pair = 0;
+            wc.pkgs[idx] = k;
+        }
+    }
+    __syncwarp();
+    if (lane == 0) {
+        sm.ws.seq = seq + 1;
+        sm.ws.log_n = 0;
+        sm.ws.log_count = 0;
+        sm.ws.pend_type = 0;
+    }
+    __syncwarp();
+}
+
+__device__ __forceinline__ int am_tile_at(uint16_t const *am16, int n) { return (int)am16[(n >> 6) * (2 * kAmStride) + (n & 63)]; }
+
+// IDLE from tile sample n on: only the noise-floor tracker moves.  Returns the first sample it could not take
+// (a trigger is conceivable there, or the tracker leaves its +-1 regime): the generic step looks at that one.
+__device__ R4_NOINLINE int idle_run(WarpSmem &sm, int n)
+{
+    constexpr int C = kChunk;
+    int const lane = threadIdx.x & 31;
+    uint16_t const *am16 = reinterpret_cast<uint16_t const *>(sm.am);
+    __syncwarp();
+    struct {
+        int low, high, lead_in;
+    } d = {sm.ws.d.low, sm.ws.d.high, sm.ws.d.lead_in};
+    Levels const lv = sm.wc.lv;
+    int const nv_tile = sm.ws.nv_tile;
+    auto am_at = [&](int i) -> int { return am_tile_at(am16, i); };
+
+    // IDLE over a long stretch, lane-parallel: see the comment in the file header and below.
+    // While |am - low| < 1024 the tracker is low += (am > low) ? +1 : -1, so low keeps the parity of
+    // (low0 + samples seen) and two trajectories of equal parity never cross and merge once the data
+    // passes between them: lane l takes chunk l, starts from a bracket [lo, hi] of the right parity that
+    // provably contains the true value, pushes both ends through its chunk and hands them to the next
+    // lane until every bracket has collapsed.  Chunks in which a trigger is conceivable (or
+    // |am - low| could reach 1024) end the stretch.
+    auto idle_tile = [&](int n) -> int {
+        if (nv_tile - n < 2 * C) return 0;
+        {
+            int hs = lv.ratio * d.low;
+            if (hs < lv.min_high) hs = lv.min_high;
+            if (d.high != hs) return 0;
+        }
+        int const c0 = n / C;
+        int const k0 = lane == c0 ? n - c0 * C : 0;
+        int k1 = nv_tile - lane * C;
+        k1 = k1 > C ? C : k1;
+        bool const in_region = lane >= c0 && k1 > k0;
+        // bounds of the chunk's AM values (of the whole chunk for the first, partial one: still bounds)
+        int const cmin = in_region ? sm.cmin[lane] : 32767, cmax = in_region ? sm.cmax[lane] : -32768;
+        int pmin = cmin, pmax = cmax; // over chunks c0..lane
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int t1 = __shfl_up_sync(0xffffffffu, pmin, o);
+            int t2 = __shfl_up_sync(0xffffffffu, pmax, o);
+            if (lane >= o) {
+                pmin = t1 < pmin ? t1 : pmin;
+                pmax = t2 > pmax ? t2 : pmax;
+            }
+        }
+        int Lmin = d.low < pmin - 1 ? d.low : pmin - 1;
+        int Lmax = d.low > pmax ? d.low : pmax;
+        int hmin = lv.ratio * Lmin;
+        if (hmin < lv.min_high) hmin = lv.min_high;
+        Thresholds th = det_thresholds(Lmin, hmin, lv);
+        bool const armed = d.lead_in + (nv_tile - n) > kLeadIn;
+        bool ok = in_region && !(armed && cmax > th.up) && (pmax - Lmin < 1024) && (Lmax - pmin < 1024);
+        unsigned bad = ~__ballot_sync(0xffffffffu, ok) & (0xffffffffu << c0);
+        int const e = bad ? __ffs(bad) - 1 : 32; // chunks c0 .. e-1 form the stretch
+        if (e - c0 < 2) return 0;
+        int const RLmin = __shfl_sync(0xffffffffu, Lmin, e - 1);
+        int const RLmax = __shfl_sync(0xffffffffu, Lmax, e - 1);
+        bool const act = lane >= c0 && lane < e;
+        int const par = (d.low + (lane * C + k0 - n)) & 1; // parity of the true value at this lane's start
+        // Start bracket.  Over K samples whose values lie in [m, M] the tracker climbs one per sample
+        // until it is >= m - 1 and falls one per sample until it is <= M, so from any start in [A, B] it
+        // ends in [min(A + K, m - 1), max(B - K, M)].  The chunk to the left has K = 64 samples (the first
+        // chunk of the stretch may be partial: then the exact start value and its real length are used).
+        int m1 = __shfl_up_sync(0xffffffffu, cmin, 1), M1 = __shfl_up_sync(0xffffffffu, cmax, 1);
+        int K1 = __shfl_up_sync(0xffffffffu, k1 - k0, 1);
+        int lo, hi;
+        if (lane == c0 + 1) {
+            lo = d.low + K1 < m1 - 1 ? d.low + K1 : m1 - 1;
+            hi = d.low - K1 > M1 ? d.low - K1 : M1;
+        } else {
+            lo = RLmin + K1 < m1 - 1 ? RLmin + K1 : m1 - 1;
+            hi = RLmax - K1 > M1 ? RLmax - K1 : M1;
+        }
+        lo = lo < RLmin ? RLmin : lo;
+        hi = hi > RLmax ? RLmax : hi;
+        lo -= (lo - par) & 1;
+        hi += (hi - par) & 1;
+        if (lane == c0) lo = hi = d.low;
+        uint16_t const *chunk = am16 + lane * (2 * kAmStride);
+        int result = 0;
+        bool done = false;
+#pragma unroll 1
+        for (int round = 0; round < 6; ++round) {
+            int elo = lo, ehi = hi;
+            if (act) {
+                if (elo == ehi) {
+#pragma unroll 4
+                    for (int k = k0; k < k1; ++k) elo += (int)chunk[k] > elo ? 1 : -1;
+                    ehi = elo;
+                } else {
+#pragma unroll 4
+                    for (int k = k0; k < k1; ++k) {
+                        int a = (int)chunk[k];
+                        elo += a > elo ? 1 : -1;
+                        ehi += a > ehi ? 1 : -1;
+                    }
+                }
+            }
+            // the true value lies inside every bracket: collapsed end brackets are the true values
+            if (__all_sync(0xffffffffu, !act || elo == ehi)) {
+                result = __shfl_sync(0xffffffffu, elo, e - 1);
+                done = true;
+                break;
+            }
+            int nlo = __shfl_up_sync(0xffffffffu, elo, 1);
+            int nhi = __shfl_up_sync(0xffffffffu, ehi, 1);
+            if (act && lane != c0) {
+                lo = nlo;
+                hi = nhi;
+            }
+        }
+        if (!done) return 0;
+        int const len = (e * C < nv_tile ? e * C : nv_tile) - n;
+        d.low = result;
+        int hh = lv.ratio * d.low;
+        d.high = hh < lv.min_high ? lv.min_high : hh;
+        int li = d.lead_in + len;
+        d.lead_in = li > kLeadIn + 1 ? kLeadIn + 1 : li;
+        return len;
+    };
+
+    // IDLE: only the noise-floor tracker moves (src/pulse_detect.c:325-334).  While
+    // |am - low| < 1024 it is low += (am > low) ? +1 : -1; with q = low + j that is
+    // q += 2 * (am_j + j > q): two dependent instructions per sample.
+    auto idle_fast = [&](int n) -> int {
+        int cnt = nv_tile - n < 32 ? nv_tile - n : 32;
+        int hs = lv.ratio * d.low;
+        if (hs < lv.min_high) hs = lv.min_high;
+        if (d.high != hs) return 0; // first IDLE sample after a package: not yet re-derived
+        int a = lane < cnt ? am_at(n + lane) : -32768;
+        int lmin = d.low - cnt;
+        int hmin = lv.ratio * lmin;
+        if (hmin < lv.min_high) hmin = lv.min_high;
+        Thresholds th = det_thresholds(lmin, hmin, lv); // lowest trigger level reachable in this chunk
+        bool armed = d.lead_in + cnt - 1 > kLeadIn;
+        bool stop = lane < cnt && ((armed && a > th.up) || (a - lmin >= 1024) || (d.low + cnt - a >= 1024));
+        unsigned m = __ballot_sync(0xffffffffu, stop);
+        if (m) {
+            int first = __ffs(m) - 1;
+            cnt = first < cnt ? first : cnt;
+        }
+        if (cnt == 0) return 0;
+        __syncwarp();
+        sm.q[lane] = a + lane;
+        __syncwarp();
+        int q = d.low;
+        int j = 0;
+        for (; j + 4 <= cnt; j += 4) {
+            int4 const b = *reinterpret_cast<int4 const *>(&sm.q[j]);
+            if (b.x > q) q += 2;
+            if (b.y > q) q += 2;
+            if (b.z > q) q += 2;
+            if (b.w > q) q += 2;
+        }
+        for (; j < cnt; ++j)
+            if (sm.q[j] > q) q += 2;
+        d.low = q - cnt;
+        int hh = lv.ratio * d.low;
+        d.high = hh < lv.min_high ? lv.min_high : hh;
+        int li = d.lead_in + cnt;
+        d.lead_in = li > kLeadIn + 1 ? kLeadIn + 1 : li;
+        return cnt;
+    };
+
+
+    while (n < nv_tile) {
+        int adv = idle_tile(n);
+        if (!adv) adv = idle_fast(n);
+        if (!adv) break;
+        n += adv;
+    }
+    __syncwarp();
+    if (lane == 0) {
+        sm.ws.d.low = d.low;
+        sm.ws.d.high = d.high;
+        sm.ws.d.lead_in = d.lead_in;
+    }
+    __syncwarp();
+    return n;
+}
+
+    // Everything of a package after its first pulse (and the first real gap), in one loop with the hot
+    // state in registers: src/pulse_detect.c:355-470 without the FSK sub-detector (it is only fed during the
+    // first pulse) and with the carrier estimate deferred (logged).
+    //   PULSE: the high-level estimator (:362-363) is a truncating 64-sample moving average -- inherently
+    //     sequential -- but the pulse only ends on a sample below the threshold its value implies.  One step
+    //     never lifts `high` above max(high, 64 * (am / 64) + 63), so the largest am of 32 samples bounds
+    //     every threshold among them from above: samples not below THAT threshold cannot end the pulse.  The
+    //     recurrence runs over exactly those (operands staged in shared memory, four per load); the first
+    //     sample that might end the pulse is then tested exactly.
+    //   GAP_START / GAP: thresholds are frozen; the next event is the first sample above `up` -- a spurious
+    //     gap if the run is still <= 10 samples, the next pulse otherwise -- or the run length reaching an
+    //     end-of-package limit (:422-470).  32 samples per ballot.
+    // Rare turns (spurious pulse, 1200 pulses) are left to det_step() in the generic step: the loop stops in front of the sample.
+    // Returns the first sample not consumed; a finished package is handed over through pend_type / pend_pos.
+__device__ R4_NOINLINE int burst_run(WarpSmem &sm, int n)
+{
+    int const lane = threadIdx.x & 31;
+    uint16_t const *am16 = reinterpret_cast<uint16_t const *>(sm.am);
+    __syncwarp();
+    struct {
+        int st, run, high, low, longest, last_pulse;
+        unsigned ook_n, ook_hw;
+        unsigned long long start_abs;
+    } d = {sm.ws.d.st, sm.ws.d.run, sm.ws.d.high, sm.ws.d.low, sm.ws.d.longest, sm.ws.d.last_pulse,
+           sm.ws.d.ook_n, sm.ws.d.ook_hw, sm.ws.d.start_abs};
+    LogRegs L = {sm.ws.log_n, sm.ws.log_start, sm.ws.log_count};
+    Levels const lv = sm.wc.lv;
+    Trains const tr = sm.wc.tr;
+    unsigned *const log = sm.wc.log;
+    int const per_ms = sm.wc.per_ms;
+    int const nv_tile = sm.ws.nv_tile;
+    unsigned long long const t0 = sm.ws.t0;
+    int pend_type = 0;
+    unsigned long long pend_pos = 0;
+    auto am_at = [&](int i) -> int { return am_tile_at(am16, i); };
+        int st = d.st, run = d.run, h = d.high;
+        int const low = d.low, minh = lv.min_high;
+#pragma unroll 1
+        while (n < nv_tile) {
+            if (st == kPulse) {
+                if (d.ook_n == 0) break; // a first pulse feeds the FSK sub-detector: not here
+                unsigned const rel = (unsigned)(t0 + (unsigned long long)n - d.start_abs);
+                // a full log is folded by the generic step first (nothing has been touched yet)
+                if (L.count && L.start + L.count != rel && L.n == kLogCap) break;
+                int cnt = nv_tile - n < 32 ? nv_tile - n : 32;
+                int const a = lane < cnt ? am_at(n + lane) : 32767;
+                int const aq = a >> 6; // am >= 0
+                int const top = __reduce_max_sync(0xffffffffu, lane < cnt ? aq : 0); // one REDUX each
+                int const bot = __reduce_min_sync(0xffffffffu, aq);
+                int hmax = 64 * top + 63;
+                hmax = h > hmax ? h : hmax;
+                unsigned const m = __ballot_sync(0xffffffffu, lane < cnt && a < det_thresholds(low, hmax, lv).down);
+                if (m) cnt = __ffs(m) - 1;
+                if (cnt) {
+                    __syncwarp();
+                    sm.q[lane] = aq;
+                    __syncwarp();
+                    int j = 0; // h >= min_high >= 0 here, so h / 64 == h >> 6
+                    if (64 * bot >= minh + 64) { // h - h/64 + q >= minh for every q >= bot when h >= minh: no clamp needed
+                        for (; j + 4 <= cnt; j += 4) {
+                            int4 const b = *reinterpret_cast<int4 const *>(&sm.q[j]);
+                            h += b.x - (int)((unsigned)h >> 6);
+                            h += b.y - (int)((unsigned)h >> 6);
+                            h += b.z - (int)((unsigned)h >> 6);
+                            h += b.w - (int)((unsigned)h >> 6);
+                        }
+                    }
+                    for (; j < cnt; ++j) {
+                        h += sm.q[j] - (int)((unsigned)h >> 6);
+                        h = h < minh ? minh : h;
+                    }
+                    log_add(L, log, rel, (unsigned)cnt, lane);
+                    run += cnt;
+                    n += cnt;
+                }
+                if (m) { // the sample at n might end the pulse: the exact test of :355
+                    int const aj = __shfl_sync(0xffffffffu, a, cnt);
+                    if (aj < det_thresholds(low, h, lv).down) {
+                        if (run + 1 < kMinPulseSamples) break; // spurious pulse (:341-350)
+                        run += 1;
+                        put(tr.ook_pulse, d.ook_hw, d.ook_n, run);
+                        d.last_pulse = run;
+                        if (run > d.longest) d.longest = run;
+                        run = 0;
+                        st = kGapStart;
+                    } else {
+                        h += (aj >> 6) - (int)((unsigned)h >> 6);
+                        h = h < minh ? minh : h;
+                        log_add(L, log, (unsigned)(t0 + (unsigned long long)n - d.start_abs), 1u, lane);
+                        run += 1;
+                    }
+                    n += 1;
+                }
+                continue;
+            }
+            // GAP_START (run <= 9 so far) or GAP
+            int const cnt = nv_tile - n;
+            int const up = det_thresholds(low, h, lv).up;
+            long long lim_a = 10ll * d.longest > 10ll * per_ms ? 10ll * d.longest : 10ll * per_ms;
+            long long const lim_b = 100ll * per_ms;
+            long long const rstar = (lim_a < lim_b ? lim_a : lim_b) + 1; // first run length that ends the package
+            long long je = rstar - run - 1;                               // ... reached at this sample of the scan
+            // the limits are only looked at in GAP, i.e. from the sample after the one that brought the run to 10
+            long long const first_gap = st == kGapStart ? (long long)(kMinPulseSamples - run) : 0;
+            if (je < first_gap) je = first_gap;
+            int const horizon = je < cnt ? (int)je + 1 : cnt; // samples that matter
+            int ja = 0x7fffffff;
+#pragma unroll 1
+            for (int base = 0; base < horizon; base += 32) {
+                int const a = base + lane < cnt ? am_at(n + base + lane) : -32768;
+                unsigned const m = __ballot_sync(0xffffffffu, a > up);
+                if (m) {
+                    ja = base + __ffs(m) - 1;
+                    break;
+                }
+            }
+            if (ja < cnt && ja <= je) {
+                if (st == kGapStart && run + ja + 1 <= kMinPulseSamples) { // spurious gap (:379-385)
+                    run += ja + 1 + d.last_pulse;
+                    st = kPulse;
+                    n += ja + 1;
+                    continue;
+                }
+                if (d.ook_n + 1 >= (unsigned)kMaxPulses) { // the 1200th pulse ends the package (:429-441): det_step()
+                    run += ja;
+                    n += ja;
+                    st = run >= kMinPulseSamples ? kGap : kGapStart;
+                    break;
+                }
+                run += ja + 1; // a new pulse starts (:422-428)
+                put(tr.ook_gap, d.ook_hw, d.ook_n, run);
+                d.ook_n += 1;
+                run = 0;
+                st = kPulse;
+                n += ja + 1;
+                continue;
+            }
+            if (je < cnt) { // end of package by gap length (:443-469)
+                run += (int)je + 1;
+                put(tr.ook_gap, d.ook_hw, d.ook_n, run);
+                d.ook_n += 1;
+                st = kIdle;
+                pend_type = 1;
+                n += (int)je; // that sample is looked at again in IDLE
+                pend_pos = t0 + (unsigned long long)n;
+                break;
+            }
+            run += cnt;
+            if (run >= kMinPulseSamples) st = kGap;
+            n += cnt;
+        }
+        d.st = st;
+        d.run = run;
+        d.high = h;
+
+    __syncwarp();
+    if (lane == 0) {
+        sm.ws.d.st = d.st;
+        sm.ws.d.run = d.run;
+        sm.ws.d.high = d.high;
+        sm.ws.d.longest = d.longest;
+        sm.ws.d.last_pulse = d.last_pulse;
+        sm.ws.d.ook_n = d.ook_n;
+        sm.ws.d.ook_hw = d.ook_hw;
+        sm.ws.log_n = L.n;
+        sm.ws.log_start = L.start;
+        sm.ws.log_count = L.count;
+        if (pend_type) {
+            sm.ws.pend_type = pend_type;
+            sm.ws.pend_pos = pend_pos;
+        }
+    }
+    __syncwarp();
+    return n;
+}
+
+// Everything else, one sample (or one stretch of a first pulse) at a time: package starts, first pulses with
+// the FSK sub-detector (they read FM), spurious pulses, the 1200th pulse, filters that rule the deferred
+// estimate out.  Always makes progress: it consumes at least one sample or hands a package over (ws.pend_type).
+template <int SS>
+__device__ R4_NOINLINE int generic_step(WarpSmem &sm, int n)
+{
+    int const lane = threadIdx.x & 31;
+    uint16_t const *am16 = reinterpret_cast<uint16_t const *>(sm.am);
+    __syncwarp();
+    DetState d = sm.ws.d;
+    LogRegs L = {sm.ws.log_n, sm.ws.log_start, sm.ws.log_count};
+    Levels const lv = sm.wc.lv;
+    Trains const tr = sm.wc.tr;
+    unsigned *const log = sm.wc.log;
+    int const per_ms = sm.wc.per_ms, fpdm = sm.wc.fpdm;
+    bool const defer_f1 = sm.wc.defer_f1 != 0, lazy_fm = sm.wc.lazy_fm != 0;
+    int const nv_tile = sm.ws.nv_tile;
+    unsigned long long const t0 = sm.ws.t0;
+    WarpCtx cx;
+    cx.lane = lane;
+    cx.nlanes = 32;
+    auto am_at = [&](int i) -> int { return am_tile_at(am16, i); };
+    auto store = [&]() {
+        __syncwarp();
+        if (lane == 0) {
+            sm.ws.d = d;
+            sm.ws.log_n = L.n;
+            sm.ws.log_start = L.start;
+            sm.ws.log_count = L.count;
+        }
+        __syncwarp();
+    };
+    auto log_append = [&](unsigned long long pos, unsigned cnt) {
+        unsigned const rel = (unsigned)(pos - d.start_abs);
+        if (log_add(L, log, rel, cnt, lane)) return;
+        store(); // the log is full: fold it into the exact value first
+        walk_f1_fold<SS>(sm);
+        d.ook_f1 = sm.ws.d.ook_f1;
+        L.n = L.count = 0;
+        log_add(L, log, rel, cnt, lane);
+    };
+    // FM of tile sample i: make the window that holds it current first
+    auto fm_need = [&](int i) {
+        unsigned long long pos = t0 + (unsigned long long)i;
+        if (sm.win_n > 0 && pos >= sm.win0 && pos < sm.win0 + (unsigned long long)sm.win_n) return;
+        fm_for_walk<SS>(sm.wc.jb, sm, pos, t0, nv_tile, lazy_fm);
+    };
+    auto fm_at = [&](int i) -> int { return (int)(int16_t)sm.fm[fm_pidx((int)(t0 + (unsigned long long)i - sm.win0))]; };
+
+    // PULSE of the FIRST pulse: the same bound, with the FSK sub-detector and the (not yet deferred)
+    // carrier estimate fed in the loop (src/pulse_detect.c:362-371).  An FSK transmission is one long OOK
+    // "pulse", so this is the hot loop of FSK captures.  Needs FM: stays inside the current window.
+    auto pulse0_fast = [&](int n) -> int {
+        int cnt = nv_tile - n < 32 ? nv_tile - n : 32;
+        int const in_win = (int)(sm.win0 + (unsigned long long)sm.win_n - (t0 + (unsigned long long)n));
+        cnt = cnt < in_win ? cnt : in_win;
+        int a = lane < cnt ? am_at(n + lane) : 32767;
+        int f = lane < cnt ? fm_at(n + lane) : 0;
+        int aq = a >> 6;
+        int const top = __reduce_max_sync(0xffffffffu, lane < cnt ? aq : 0);
+        int hmax = 64 * top + 63;
+        hmax = d.high > hmax ? d.high : hmax;
+        Thresholds th = det_thresholds(d.low, hmax, lv);
+        unsigned m = __ballot_sync(0xffffffffu, lane < cnt && a < th.down);
+        if (m) cnt = __ffs(m) - 1;
+        if (cnt == 0) return 0;
+        int const minh = lv.min_high;
+#pragma unroll 1
+        for (int j = 0; j < cnt; ++j) {
+            int aj = __shfl_sync(0xffffffffu, aq, j);
+            int fj = __shfl_sync(0xffffffffu, f, j);
+            d.high += aj - (int)((unsigned)d.high >> 6);
+            d.high = d.high < minh ? minh : d.high;
+            d.ook_f1 += fj / 64 - d.ook_f1 / 64;
+            if (fpdm == 0)
+                fsk_classic(d, tr, fj, cx);
+            else
+                fsk_minmax(d, tr, fj, cx);
+        }
+        d.run += cnt;
+        return cnt;
+    };
+
+
+    // inside a first pulse (and its GAP_START) the FSK sub-detector and the undeferred estimate read FM
+    bool const first = d.ook_n == 0 && (d.st == kPulse || d.st == kGapStart);
+    bool const wants_fm = first || (d.st == kPulse && !defer_f1);
+    if (wants_fm) fm_need(n);
+    int adv = 0;
+    if (first && d.st == kPulse) adv = pulse0_fast(n);
+    if (!adv) {
+        // every lane runs the (warp-uniform) step and writes the same train entries: keep the lanes
+        // together so that no lane reads an entry another lane has already overwritten for a later sample
+        __syncwarp();
+        int const r = det_step<kStepAll>(d, lv, tr, am_at(n), wants_fm ? fm_at(n) : 0, t0 + n, per_ms, fpdm, cx, defer_f1);
+        if (r & kStepF1Deferred) log_append(t0 + (unsigned long long)n, 1u);
+        if (r & 3) {
+            // the same sample is examined again, now in IDLE
+            __syncwarp();
+            if (lane == 0) {
+                sm.ws.pend_type = r & 3;
+                sm.ws.pend_pos = t0 + (unsigned long long)n;
+            }
+        } else {
+            if (d.st == kPulse && d.run == 0 && d.ook_n == 0) L.n = L.count = 0; // a package has just begun
+            adv = 1;
+        }
+    }
+    store();
+    return n + adv;
+}
+
 // --------------------------------------------------------------------------- kernel ------
 
 template <int SS>
 __global__ void __launch_bounds__(kDetectWarps * 32, kDetectCtasPerSm) k_detect(DetectParams p)
 {
-    constexpr int SPL = 16 / SS;
     constexpr int C = kChunk;
     constexpr int T = kTile;
     R4_DYN_SMEM(uint32_t, smem_raw);
@@ -551,159 +1183,73 @@ __global__ void __launch_bounds__(kDetectWarps * 32, kDetectCtasPerSm) k_detect(
     uint8_t const *const src = p.data + byte0;
     int16_t *const am_stream = p.am + p.am_offsets[s];
     ChunkInfo const *const chunk_stream = p.chunks + p.am_offsets[s] / kChunk;
-
-    Trains tr;
-    tr.ook_pulse = p.train_scratch + (size_t)s * kTrainInts;
-    tr.ook_gap = tr.ook_pulse + kMaxPulses;
-    tr.fsk_pulse = tr.ook_gap + kMaxPulses;
-    tr.fsk_gap = tr.fsk_pulse + kMaxPulses;
-    unsigned *const log = p.log_scratch + (size_t)s * kLogCap * 2;
-
-    WarpCtx cx;
-    cx.lane = lane;
-    cx.nlanes = 32;
-
-    FmJob<SS> jb;
-    jb.src = src;
-    jb.N = N;
-    jb.flip = p.flip;
-    jb.a1 = p.fm_a1;
-    jb.b0 = p.fm_b0;
-    jb.fm_on = p.enable_fm;
-    jb.use_mag = p.use_mag;
-    jb.monotone = p.wrap_free;
-    jb.fm_out = p.fm_out ? p.fm_out + byte0 / SS : nullptr;
     // FM windows on demand need the rigorous state rebuild (monotone filter); the stage dump wants every sample
     bool const lazy_fm = !fm_on || (p.wrap_free && p.lazy_fm && !p.want_stages);
     // the deferred carrier estimate re-makes FM for logged samples later: needs the state rebuild as well
     bool const defer_f1 = !fm_on || p.wrap_free != 0;
 
-    DetState d;
-    unsigned seq = 0;
-    int const per_ms = (int)(p.rate / 1000);
     int y_am = 0; // the last AM value of the previous tile: the AM filter state (reset_sdr_flow(): zero)
     int flushed = 0;
-    unsigned log_n = 0, log_start = 0, log_count = 0; // deferred carrier-estimate log: closed entries, the open entry
-    if (p.first_chunk) {
-        det_reset(d);
-        d.ook_hw = d.fsk_hw = kMaxPulses; // scratch is not assumed to be zero: first package clears it
-        if (lane == 0) {
+    if (lane == 0) {
+        WalkConst &wc = sm.wc;
+        wc.jb.src = src;
+        wc.jb.N = N;
+        wc.jb.flip = p.flip;
+        wc.jb.a1 = p.fm_a1;
+        wc.jb.b0 = p.fm_b0;
+        wc.jb.fm_on = p.enable_fm;
+        wc.jb.use_mag = p.use_mag;
+        wc.jb.monotone = p.wrap_free;
+        wc.jb.fm_out = p.fm_out ? p.fm_out + byte0 / SS : nullptr;
+        wc.tr.ook_pulse = p.train_scratch + (size_t)s * kTrainInts;
+        wc.tr.ook_gap = wc.tr.ook_pulse + kMaxPulses;
+        wc.tr.fsk_pulse = wc.tr.ook_gap + kMaxPulses;
+        wc.tr.fsk_gap = wc.tr.fsk_pulse + kMaxPulses;
+        wc.log = p.log_scratch + (size_t)s * kLogCap * 2;
+        wc.lv = p.lv;
+        wc.per_ms = (int)(p.rate / 1000);
+        wc.fpdm = p.fpdm;
+        wc.lazy_fm = lazy_fm;
+        wc.defer_f1 = defer_f1;
+        wc.stream = s;
+        wc.block_samples = p.block_samples;
+        wc.pkgs = p.pkgs;
+        wc.pulse_pool = p.pulse_pool;
+        wc.gap_pool = p.gap_pool;
+        wc.pkg_cap = p.pkg_cap;
+        wc.pool_cap = p.pool_cap;
+        wc.counters = p.counters;
+        WalkState &ws = sm.ws;
+        ws.pend_type = 0;
+        ws.pend_pos = 0;
+        ws.t0 = 0;
+        ws.nv_tile = 0;
+        if (p.first_chunk) {
+            det_reset(ws.d);
+            ws.d.ook_hw = ws.d.fsk_hw = kMaxPulses; // scratch is not assumed to be zero: first package clears it
+            ws.log_n = ws.log_start = ws.log_count = 0;
+            ws.seq = 0;
             sm.fm_pos = 0;
             sm.fm_y = sm.fm_xf = 0;
-        }
-    } else {
-        StreamState const &ss = p.state[s];
-        d = ss.d;
-        y_am = ss.y_am;
-        seq = ss.seq;
-        flushed = ss.flushed;
-        if (lane == 0) {
+        } else {
+            StreamState const &ss = p.state[s];
+            ws.d = ss.d;
+            ws.seq = ss.seq;
+            ws.log_n = ss.log_n;
+            ws.log_start = ss.last_start;
+            ws.log_count = ss.last_count;
             sm.fm_pos = ss.fm_pos;
             sm.fm_y = ss.fm_y;
             sm.fm_xf = ss.fm_xf;
         }
-        log_n = ss.log_n;
-        log_start = ss.last_start;
-        log_count = ss.last_count;
-    }
-    if (lane == 0) {
         sm.win0 = 0;
         sm.win_n = 0;
     }
+    if (!p.first_chunk) {
+        y_am = p.state[s].y_am;
+        flushed = p.state[s].flushed;
+    }
     __syncwarp();
-
-    // eager mode: put the contiguous end-of-tile filter state back after windows were (re-)made out of order
-    auto restore_tile_end = [&]() {
-        __syncwarp();
-        if (lane == 0 && !lazy_fm) {
-            sm.fm_pos = sm.tile_end_pos;
-            sm.fm_y = sm.tile_end_y;
-            sm.fm_xf = sm.tile_end_xf;
-        }
-        __syncwarp();
-    };
-
-    // ---- deferred carrier estimate: log of updating samples ---------------------------------
-    // Entries are runs of consecutive updating samples (relative to the package start).  The open entry
-    // lives in registers (warp-uniform); closed ones go to the stream's log in global memory.
-    auto f1_fold = [&]() { // everything logged so far into the exact value d.ook_f1
-        int g = f1_evaluate<SS>(jb, sm, log, d.start_abs, d.ook_f1, log_n, log_start, log_count);
-        restore_tile_end();
-        d.ook_f1 = g;
-        log_n = 0;
-        log_count = 0;
-    };
-    auto log_append = [&](unsigned long long pos, unsigned cnt) {
-        unsigned rel = (unsigned)(pos - d.start_abs);
-        if (log_count && log_start + log_count == rel) {
-            log_count += cnt;
-            return;
-        }
-        if (log_count) { // close the open entry
-            if (log_n == kLogCap) {
-                f1_fold();
-            } else {
-                if (lane == 0) {
-                    log[2 * log_n] = log_start;
-                    log[2 * log_n + 1] = log_count;
-                }
-                log_n += 1;
-            }
-        }
-        log_start = rel;
-        log_count = cnt;
-    };
-    auto log_clear = [&]() { log_n = log_count = 0; };
-
-    auto emit = [&](int type, unsigned long long pos, bool flush) {
-        if (type == 1 && (log_n || log_count)) f1_fold(); // the carrier estimate of an OOK package is read now
-        log_clear();
-        PackageHeader h = package_header(d, type);
-        unsigned cnt = h.num_pulses + 1 < (unsigned)kMaxPulses ? h.num_pulses + 1 : (unsigned)kMaxPulses;
-        unsigned idx = 0, off = 0;
-        if (lane == 0) {
-            idx = atomicAdd(&p.counters[0], 1u);
-            off = atomicAdd(&p.counters[1], cnt);
-        }
-        idx = __shfl_sync(0xffffffffu, idx, 0);
-        off = __shfl_sync(0xffffffffu, off, 0);
-        bool fits = idx < p.pkg_cap && (unsigned long long)off + cnt <= p.pool_cap;
-        if (!fits) {
-            if (lane == 0) atomicOr(&p.counters[2], 1u);
-        } else {
-            __syncwarp();
-            int const *sp = type == 1 ? tr.ook_pulse : tr.fsk_pulse;
-            int const *sg = type == 1 ? tr.ook_gap : tr.fsk_gap;
-            for (unsigned i = lane; i < cnt; i += 32) {
-                p.pulse_pool[off + i] = sp[i];
-                p.gap_pool[off + i] = sg[i];
-            }
-            if (lane == 0) {
-                unsigned long long blk = flush ? (N + p.block_samples - 1) / p.block_samples : pos / p.block_samples;
-                unsigned long long bstart = blk * p.block_samples;
-                unsigned long long blen = flush ? 0 : (N - bstart < p.block_samples ? N - bstart : p.block_samples);
-                r433b_package k;
-                k.stream = s;
-                k.seq = seq;
-                k.type = type;
-                k.block = (int)blk;
-                k.offset = h.offset;
-                k.end_pos = pos;
-                k.start_ago = flush ? (unsigned)(N - h.start_abs) : (unsigned)(bstart + blen - h.start_abs);
-                k.end_ago = flush ? 0u : (unsigned)(blen - (pos - bstart));
-                k.num_pulses = h.num_pulses;
-                k.pulse_off = off;
-                k.pulse_count = cnt;
-                k.ook_low_estimate = h.low;
-                k.ook_high_estimate = h.high;
-                k.fsk_f1_est = h.f1;
-                k.fsk_f2_est = h.f2;
-                k.first_pair = 0;
-                p.pkgs[idx] = k;
-            }
-        }
-        seq++;
-    };
 
     int const a1 = p.lpf_a1, b0 = p.lpf_b0;
 
@@ -732,6 +1278,10 @@ __global__ void __launch_bounds__(kDetectWarps * 32, kDetectCtasPerSm) k_detect(
             bool const has = lane * C < nv_tile;
             sm.cmin[lane] = has ? (int)ci.cmin : 32767;
             sm.cmax[lane] = has ? (int)ci.cmax : 0;
+            if (lane == 0) {
+                sm.ws.t0 = t0;
+                sm.ws.nv_tile = nv_tile;
+            }
         }
         __syncwarp();
         // hand-over check (see the file header): the first tile of a stream starts from the reset state in k_front
@@ -746,10 +1296,7 @@ __global__ void __launch_bounds__(kDetectWarps * 32, kDetectCtasPerSm) k_detect(
                 if (lane == 0) atomicAdd(&p.counters[5], 1u);
             }
         }
-        y_am = (int)(int16_t)am16[((nv_tile - 1) >> 6) * (2 * kAmStride) + ((nv_tile - 1) & 63)];
-        // The (warp-uniform) detector state is not needed by the FM tile pass: park it so its loops have the registers.
-        if (lane == 0) sm.park = d;
-        __syncwarp();
+        y_am = am_tile_at(am16, nv_tile - 1);
         // ---- FM for the whole tile when it cannot be made on demand -----------------------------
         if (!lazy_fm || (!fm_on && p.fm_out)) {
             for (int w = 0; w * kFmWin < nv_tile; ++w) {
@@ -759,7 +1306,7 @@ __global__ void __launch_bounds__(kDetectWarps * 32, kDetectCtasPerSm) k_detect(
                 }
                 __syncwarp();
                 int n = nv_tile - w * kFmWin < kFmWin ? nv_tile - w * kFmWin : kFmWin;
-                fm_window<SS>(jb, sm, t0 + (unsigned long long)w * kFmWin, n);
+                fm_window<SS>(sm.wc.jb, sm, t0 + (unsigned long long)w * kFmWin, n);
             }
             if (lane == 0) {
                 sm.tile_end_pos = sm.fm_pos;
@@ -768,371 +1315,22 @@ __global__ void __launch_bounds__(kDetectWarps * 32, kDetectCtasPerSm) k_detect(
             }
             __syncwarp();
         }
-        d = sm.park;
 
-        // FM of tile sample n: make the window that holds it current first
-        auto fm_need = [&](int n) {
-            unsigned long long pos = t0 + (unsigned long long)n;
-            if (sm.win_n > 0 && pos >= sm.win0 && pos < sm.win0 + (unsigned long long)sm.win_n) return;
-            fm_for_walk<SS>(jb, sm, pos, t0, nv_tile, lazy_fm);
-        };
-        auto am_at = [&](int n) -> int { return (int)am16[(n >> 6) * (2 * kAmStride) + (n & 63)]; };
-        auto fm_at = [&](int n) -> int { return (int)(int16_t)sm.fm[fm_pidx((int)(t0 + (unsigned long long)n - sm.win0))]; };
-
-        // ---- package detector over the tile (warp-uniform) -------------------------------
-        if (t0 % p.block_samples == 0) det_call_boundary(d, p.lv);
-        int pend_type = 0; // a package to hand over (set by the GAP scan or by det_step), at stream position pend_pos
-        unsigned long long pend_pos = 0;
-
-        // IDLE over a long stretch, lane-parallel: see the comment in the file header and below.
-        // While |am - low| < 1024 the tracker is low += (am > low) ? +1 : -1, so low keeps the parity of
-        // (low0 + samples seen) and two trajectories of equal parity never cross and merge once the data
-        // passes between them: lane l takes chunk l, starts from a bracket [lo, hi] of the right parity that
-        // provably contains the true value, pushes both ends through its chunk and hands them to the next
-        // lane until every bracket has collapsed.  Chunks in which a trigger is conceivable (or
-        // |am - low| could reach 1024) end the stretch.
-        auto idle_tile = [&](int n) -> int {
-            if (nv_tile - n < 2 * C) return 0;
-            {
-                int hs = p.lv.ratio * d.low;
-                if (hs < p.lv.min_high) hs = p.lv.min_high;
-                if (d.high != hs) return 0;
-            }
-            int const c0 = n / C;
-            int const k0 = lane == c0 ? n - c0 * C : 0;
-            int k1 = nv_tile - lane * C;
-            k1 = k1 > C ? C : k1;
-            bool const in_region = lane >= c0 && k1 > k0;
-            // bounds of the chunk's AM values (of the whole chunk for the first, partial one: still bounds)
-            int const cmin = in_region ? sm.cmin[lane] : 32767, cmax = in_region ? sm.cmax[lane] : -32768;
-            int pmin = cmin, pmax = cmax; // over chunks c0..lane
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                int t1 = __shfl_up_sync(0xffffffffu, pmin, o);
-                int t2 = __shfl_up_sync(0xffffffffu, pmax, o);
-                if (lane >= o) {
-                    pmin = t1 < pmin ? t1 : pmin;
-                    pmax = t2 > pmax ? t2 : pmax;
-                }
-            }
-            int Lmin = d.low < pmin - 1 ? d.low : pmin - 1;
-            int Lmax = d.low > pmax ? d.low : pmax;
-            int hmin = p.lv.ratio * Lmin;
-            if (hmin < p.lv.min_high) hmin = p.lv.min_high;
-            Thresholds th = det_thresholds(Lmin, hmin, p.lv);
-            bool const armed = d.lead_in + (nv_tile - n) > kLeadIn;
-            bool ok = in_region && !(armed && cmax > th.up) && (pmax - Lmin < 1024) && (Lmax - pmin < 1024);
-            unsigned bad = ~__ballot_sync(0xffffffffu, ok) & (0xffffffffu << c0);
-            int const e = bad ? __ffs(bad) - 1 : 32; // chunks c0 .. e-1 form the stretch
-            if (e - c0 < 2) return 0;
-            int const RLmin = __shfl_sync(0xffffffffu, Lmin, e - 1);
-            int const RLmax = __shfl_sync(0xffffffffu, Lmax, e - 1);
-            bool const act = lane >= c0 && lane < e;
-            int const par = (d.low + (lane * C + k0 - n)) & 1; // parity of the true value at this lane's start
-            // Start bracket.  Over K samples whose values lie in [m, M] the tracker climbs one per sample
-            // until it is >= m - 1 and falls one per sample until it is <= M, so from any start in [A, B] it
-            // ends in [min(A + K, m - 1), max(B - K, M)].  The chunk to the left has K = 64 samples (the first
-            // chunk of the stretch may be partial: then the exact start value and its real length are used).
-            int m1 = __shfl_up_sync(0xffffffffu, cmin, 1), M1 = __shfl_up_sync(0xffffffffu, cmax, 1);
-            int K1 = __shfl_up_sync(0xffffffffu, k1 - k0, 1);
-            int lo, hi;
-            if (lane == c0 + 1) {
-                lo = d.low + K1 < m1 - 1 ? d.low + K1 : m1 - 1;
-                hi = d.low - K1 > M1 ? d.low - K1 : M1;
-            } else {
-                lo = RLmin + K1 < m1 - 1 ? RLmin + K1 : m1 - 1;
-                hi = RLmax - K1 > M1 ? RLmax - K1 : M1;
-            }
-            lo = lo < RLmin ? RLmin : lo;
-            hi = hi > RLmax ? RLmax : hi;
-            lo -= (lo - par) & 1;
-            hi += (hi - par) & 1;
-            if (lane == c0) lo = hi = d.low;
-            uint16_t const *chunk = am16 + lane * (2 * kAmStride);
-            int result = 0;
-            bool done = false;
-#pragma unroll 1
-            for (int round = 0; round < 6; ++round) {
-                int elo = lo, ehi = hi;
-                if (act) {
-                    if (elo == ehi) {
-#pragma unroll 4
-                        for (int k = k0; k < k1; ++k) elo += (int)chunk[k] > elo ? 1 : -1;
-                        ehi = elo;
-                    } else {
-#pragma unroll 4
-                        for (int k = k0; k < k1; ++k) {
-                            int a = (int)chunk[k];
-                            elo += a > elo ? 1 : -1;
-                            ehi += a > ehi ? 1 : -1;
-                        }
-                    }
-                }
-                // the true value lies inside every bracket: collapsed end brackets are the true values
-                if (__all_sync(0xffffffffu, !act || elo == ehi)) {
-                    result = __shfl_sync(0xffffffffu, elo, e - 1);
-                    done = true;
-                    break;
-                }
-                int nlo = __shfl_up_sync(0xffffffffu, elo, 1);
-                int nhi = __shfl_up_sync(0xffffffffu, ehi, 1);
-                if (act && lane != c0) {
-                    lo = nlo;
-                    hi = nhi;
-                }
-            }
-            if (!done) return 0;
-            int const len = (e * C < nv_tile ? e * C : nv_tile) - n;
-            d.low = result;
-            int hh = p.lv.ratio * d.low;
-            d.high = hh < p.lv.min_high ? p.lv.min_high : hh;
-            int li = d.lead_in + len;
-            d.lead_in = li > kLeadIn + 1 ? kLeadIn + 1 : li;
-            return len;
-        };
-
-        // IDLE: only the noise-floor tracker moves (src/pulse_detect.c:325-334).  While
-        // |am - low| < 1024 it is low += (am > low) ? +1 : -1; with q = low + j that is
-        // q += 2 * (am_j + j > q): two dependent instructions per sample.
-        auto idle_fast = [&](int n) -> int {
-            int cnt = nv_tile - n < 32 ? nv_tile - n : 32;
-            int hs = p.lv.ratio * d.low;
-            if (hs < p.lv.min_high) hs = p.lv.min_high;
-            if (d.high != hs) return 0; // first IDLE sample after a package: not yet re-derived
-            int a = lane < cnt ? am_at(n + lane) : -32768;
-            int lmin = d.low - cnt;
-            int hmin = p.lv.ratio * lmin;
-            if (hmin < p.lv.min_high) hmin = p.lv.min_high;
-            Thresholds th = det_thresholds(lmin, hmin, p.lv); // lowest trigger level reachable in this chunk
-            bool armed = d.lead_in + cnt - 1 > kLeadIn;
-            bool stop = lane < cnt && ((armed && a > th.up) || (a - lmin >= 1024) || (d.low + cnt - a >= 1024));
-            unsigned m = __ballot_sync(0xffffffffu, stop);
-            if (m) {
-                int first = __ffs(m) - 1;
-                cnt = first < cnt ? first : cnt;
-            }
-            if (cnt == 0) return 0;
-            __syncwarp();
-            sm.q[lane] = a + lane;
-            __syncwarp();
-            int q = d.low;
-            int j = 0;
-            for (; j + 4 <= cnt; j += 4) {
-                int4 const b = *reinterpret_cast<int4 const *>(&sm.q[j]);
-                if (b.x > q) q += 2;
-                if (b.y > q) q += 2;
-                if (b.z > q) q += 2;
-                if (b.w > q) q += 2;
-            }
-            for (; j < cnt; ++j)
-                if (sm.q[j] > q) q += 2;
-            d.low = q - cnt;
-            int hh = p.lv.ratio * d.low;
-            d.high = hh < p.lv.min_high ? p.lv.min_high : hh;
-            int li = d.lead_in + cnt;
-            d.lead_in = li > kLeadIn + 1 ? kLeadIn + 1 : li;
-            return cnt;
-        };
-
-        // GAP: thresholds are frozen; the next event is the first sample above `up` or the run length
-        // reaching an end-of-package limit (src/pulse_detect.c:422-470).  Look for either in the rest of the
-        // tile, 32 samples per ballot.
-        auto gap_fast = [&](int n) -> int {
-            if (d.eop_flag) return 0;
-            int const cnt = nv_tile - n;
-            Thresholds th = det_thresholds(d.low, d.high, p.lv);
-            long long lim_a = 10ll * d.longest > 10ll * per_ms ? 10ll * d.longest : 10ll * per_ms;
-            long long lim_b = 100ll * per_ms;
-            long long rstar = (lim_a < lim_b ? lim_a : lim_b) + 1; // first run length that ends the package
-            long long je = rstar - d.run - 1;
-            if (je < 0) je = 0;
-            int const horizon = je < cnt ? (int)je + 1 : cnt; // samples that matter
-            int ja = 0x7fffffff;
-#pragma unroll 1
-            for (int base = 0; base < horizon; base += 32) {
-                int a = base + lane < cnt ? am_at(n + base + lane) : -32768;
-                unsigned m = __ballot_sync(0xffffffffu, a > th.up);
-                if (m) {
-                    ja = base + __ffs(m) - 1;
-                    break;
-                }
-            }
-            if (ja < cnt && ja <= je) { // a new pulse starts first
-                d.run += ja + 1;
-                put(tr.ook_gap, d.ook_hw, d.ook_n, d.run);
-                d.ook_n += 1;
-                if (d.ook_n >= (unsigned)kMaxPulses) {
-                    d.st = kIdle;
-                    pend_type = 1;
-                    pend_pos = t0 + (unsigned long long)(n + ja);
-                    return ja; // that sample is looked at again in IDLE
-                }
-                d.run = 0;
-                d.st = kPulse;
-                return ja + 1;
-            }
-            if (je < cnt) { // end of package by gap length
-                d.run += (int)je + 1;
-                put(tr.ook_gap, d.ook_hw, d.ook_n, d.run);
-                d.ook_n += 1;
-                d.st = kIdle;
-                pend_type = 1;
-                pend_pos = t0 + (unsigned long long)(n + (int)je);
-                return (int)je;
-            }
-            d.run += cnt;
-            return cnt;
-        };
-
-        // PULSE after the first pulse: the high-level estimator (src/pulse_detect.c:362-363) is a truncating
-        // 64-sample moving average -- inherently sequential -- but the pulse only ends on a sample below the
-        // threshold its value implies.  One step never lifts `high` above max(high, 64 * (am / 64) + 63), so
-        // the largest am of the chunk bounds every threshold of the chunk from above: samples not below THAT
-        // threshold cannot end the pulse.  The recurrence runs over exactly those (operands staged in shared
-        // memory, four per load); the carrier estimate of those samples is deferred (logged).  The first
-        // sample that might end the pulse is left to det_step(), which tests it exactly.
-        auto pulse_fast = [&](int n) -> int {
-            int cnt = nv_tile - n < 32 ? nv_tile - n : 32;
-            if (!defer_f1) { // FM is read here: stay inside the current window
-                int const in_win = (int)(sm.win0 + (unsigned long long)sm.win_n - (t0 + (unsigned long long)n));
-                cnt = cnt < in_win ? cnt : in_win;
-            }
-            int a = lane < cnt ? am_at(n + lane) : 32767;
-            int aq = a >> 6; // am >= 0
-            int const top = __reduce_max_sync(0xffffffffu, lane < cnt ? aq : 0); // one REDUX each
-            int const bot = __reduce_min_sync(0xffffffffu, aq);
-            int hmax = 64 * top + 63;
-            hmax = d.high > hmax ? d.high : hmax;
-            Thresholds th = det_thresholds(d.low, hmax, p.lv);
-            unsigned m = __ballot_sync(0xffffffffu, lane < cnt && a < th.down);
-            if (m) cnt = __ffs(m) - 1;
-            if (cnt == 0) return 0;
-            __syncwarp();
-            sm.q[lane] = aq;
-            __syncwarp();
-            int h = d.high; // h >= min_high >= 0 here, so h / 64 == h >> 6
-            int const minh = p.lv.min_high;
-            int j = 0;
-            if (64 * bot >= minh + 64) { // h - h/64 + q >= minh for every q >= bot when h >= minh: no clamp needed
-                for (; j + 4 <= cnt; j += 4) {
-                    int4 const b = *reinterpret_cast<int4 const *>(&sm.q[j]);
-                    h += b.x - (int)((unsigned)h >> 6);
-                    h += b.y - (int)((unsigned)h >> 6);
-                    h += b.z - (int)((unsigned)h >> 6);
-                    h += b.w - (int)((unsigned)h >> 6);
-                }
-            }
-            for (; j < cnt; ++j) {
-                h += sm.q[j] - (int)((unsigned)h >> 6);
-                h = h < minh ? minh : h;
-            }
-            d.high = h;
-            if (defer_f1) {
-                log_append(t0 + (unsigned long long)n, (unsigned)cnt);
-            } else {
-                int f = lane < cnt ? fm_at(n + lane) : 0;
-                int g = d.ook_f1;
-#pragma unroll 1
-                for (int k = 0; k < cnt; ++k) g = f1_step(g, __shfl_sync(0xffffffffu, f, k));
-                d.ook_f1 = g;
-            }
-            d.run += cnt;
-            return cnt;
-        };
-
-        // PULSE of the FIRST pulse: the same bound, with the FSK sub-detector and the (not yet deferred)
-        // carrier estimate fed in the loop (src/pulse_detect.c:362-371).  An FSK transmission is one long OOK
-        // "pulse", so this is the hot loop of FSK captures.  Needs FM: stays inside the current window.
-        auto pulse0_fast = [&](int n) -> int {
-            int cnt = nv_tile - n < 32 ? nv_tile - n : 32;
-            int const in_win = (int)(sm.win0 + (unsigned long long)sm.win_n - (t0 + (unsigned long long)n));
-            cnt = cnt < in_win ? cnt : in_win;
-            int a = lane < cnt ? am_at(n + lane) : 32767;
-            int f = lane < cnt ? fm_at(n + lane) : 0;
-            int aq = a >> 6;
-            int const top = __reduce_max_sync(0xffffffffu, lane < cnt ? aq : 0);
-            int hmax = 64 * top + 63;
-            hmax = d.high > hmax ? d.high : hmax;
-            Thresholds th = det_thresholds(d.low, hmax, p.lv);
-            unsigned m = __ballot_sync(0xffffffffu, lane < cnt && a < th.down);
-            if (m) cnt = __ffs(m) - 1;
-            if (cnt == 0) return 0;
-            int const minh = p.lv.min_high;
-#pragma unroll 1
-            for (int j = 0; j < cnt; ++j) {
-                int aj = __shfl_sync(0xffffffffu, aq, j);
-                int fj = __shfl_sync(0xffffffffu, f, j);
-                d.high += aj - (int)((unsigned)d.high >> 6);
-                d.high = d.high < minh ? minh : d.high;
-                d.ook_f1 += fj / 64 - d.ook_f1 / 64;
-                if (p.fpdm == 0)
-                    fsk_classic(d, tr, fj, cx);
-                else
-                    fsk_minmax(d, tr, fj, cx);
-            }
-            d.run += cnt;
-            return cnt;
-        };
-
-        // GAP_START after the first pulse (no FSK feed): thresholds are frozen and nothing happens until
-        // either a sample rises above `up` (spurious gap) or the run reaches 10 samples.  Skip the uneventful
-        // samples in front of that transition; det_step() takes the transition.
-        auto gapstart_fast = [&](int n) -> int {
-            int quiet = kMinPulseSamples - 1 - d.run; // samples that can pass without reaching 10
-            if (quiet <= 0) return 0;
-            int cnt = nv_tile - n < quiet ? nv_tile - n : quiet;
-            Thresholds th = det_thresholds(d.low, d.high, p.lv);
-            int a = lane < cnt ? am_at(n + lane) : -32768;
-            unsigned m = __ballot_sync(0xffffffffu, lane < cnt && a > th.up);
-            if (m) {
-                int ja = __ffs(m) - 1;
-                cnt = ja < cnt ? ja : cnt;
-            }
-            d.run += cnt;
-            return cnt;
-        };
-
+        // ---- package detector over the tile (warp-uniform), phase by phase ------------------------
+        if (t0 % p.block_samples == 0) walk_call_boundary(sm);
         for (int n = 0; n < nv_tile;) {
-            // inside a first pulse (and its GAP_START) the FSK sub-detector and the undeferred estimate read FM
-            bool const first = d.ook_n == 0 && (d.st == kPulse || d.st == kGapStart);
-            bool const wants_fm = first || (d.st == kPulse && !defer_f1);
-            if (wants_fm) fm_need(n);
-            int adv = 0;
-            if (d.st == kIdle) {
-                adv = idle_tile(n);
-                if (!adv) adv = idle_fast(n);
-            } else if (d.st == kGap) {
-                adv = gap_fast(n);
-            } else if (d.st == kPulse) {
-                adv = d.ook_n ? pulse_fast(n) : pulse0_fast(n);
-            } else if (d.ook_n) {
-                adv = gapstart_fast(n);
+            int const st = sm.ws.d.st;
+            int m = n;
+            if (st == kIdle)
+                m = idle_run(sm, n);
+            else if (defer_f1 && !sm.ws.d.eop_flag && (sm.ws.d.ook_n != 0 || st == kGap))
+                m = burst_run(sm, n);
+            if (m == n && !sm.ws.pend_type) m = generic_step<SS>(sm, n);
+            n = m;
+            if (sm.ws.pend_type) { // a package to hand over; the sample at n is looked at again
+                walk_emit<SS>(sm, sm.ws.pend_type, sm.ws.pend_pos, false);
+                walk_call_boundary(sm);
             }
-            if (!adv && !pend_type) {
-                // every lane runs the (warp-uniform) step and writes the same train entries: keep the lanes
-                // together so that no lane reads an entry another lane has already overwritten for a later sample
-                __syncwarp();
-                int const a = am_at(n);
-                int r;
-                if (first)
-                    r = det_step<kStepFirst>(d, p.lv, tr, a, fm_at(n), t0 + n, per_ms, p.fpdm, cx, defer_f1);
-                else
-                    r = det_step<kStepLean>(d, p.lv, tr, a, wants_fm ? fm_at(n) : 0, t0 + n, per_ms, p.fpdm, cx, defer_f1);
-                if (r & kStepF1Deferred) log_append(t0 + (unsigned long long)n, 1u);
-                if (r & 3) {
-                    pend_type = r & 3; // the same sample is examined again, now in IDLE
-                    pend_pos = t0 + (unsigned long long)n;
-                } else {
-                    if (d.st == kPulse && d.run == 0 && d.ook_n == 0) log_clear(); // a package has just begun
-                    adv = 1;
-                }
-            }
-            if (pend_type) {
-                emit(pend_type, pend_pos, false);
-                det_call_boundary(d, p.lv);
-                pend_type = 0;
-            }
-            n += adv;
         }
         __syncwarp();
     }
@@ -1140,24 +1338,29 @@ __global__ void __launch_bounds__(kDetectWarps * 32, kDetectCtasPerSm) k_detect(
     // flush_sdr_flow(): len == 0 call(s) at the end of the file, in the launch that reaches it
     if (N <= p.sample_end && !flushed) {
         for (;;) {
-            int ev = det_flush(d, tr, p.fpdm);
+            __syncwarp();
+            DetState d = sm.ws.d;
+            int const ev = det_flush(d, sm.wc.tr, p.fpdm);
+            __syncwarp();
+            if (lane == 0) sm.ws.d = d;
+            __syncwarp();
             if (!ev) break;
-            emit(ev, N, true);
+            walk_emit<SS>(sm, ev, N, true);
         }
         flushed = 1;
     }
     __syncwarp();
     if (lane == 0 && p.state) {
         StreamState &ss = p.state[s];
-        ss.d = d;
+        ss.d = sm.ws.d;
         ss.y_am = y_am;
         ss.fm_pos = sm.fm_pos;
         ss.fm_y = sm.fm_y;
         ss.fm_xf = sm.fm_xf;
-        ss.log_n = log_n;
-        ss.last_start = log_start;
-        ss.last_count = log_count;
-        ss.seq = seq;
+        ss.log_n = sm.ws.log_n;
+        ss.last_start = sm.ws.log_start;
+        ss.last_count = sm.ws.log_count;
+        ss.seq = sm.ws.seq;
         ss.flushed = flushed;
     }
 }
