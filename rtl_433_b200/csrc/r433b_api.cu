@@ -154,6 +154,11 @@ int r433b_create(int cuda_device, r433b_ctx **out)
         delete ctx;
         return R433B_ECUDA;
     }
+    // both kernels live on shared memory (staged IQ tiles, AM tiles + walk state): ask for the largest carve-out
+    cudaFuncSetAttribute((void const *)k_front<2>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    cudaFuncSetAttribute((void const *)k_front<4>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    cudaFuncSetAttribute((void const *)k_detect<2>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    cudaFuncSetAttribute((void const *)k_detect<4>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     for (auto &v : ctx->ev) cudaEventCreate(&v);
     cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking);
     cudaStreamCreateWithFlags(&ctx->s_det, cudaStreamNonBlocking);
@@ -398,7 +403,8 @@ int r433b_process(r433b_ctx *ctx, r433b_batch const *b)
             uint64_t const warps = (uint64_t)q.n_streams * fp.tiles;
             unsigned const fgrid = (unsigned)((warps + kFrontWarps - 1) / kFrontWarps);
             void (*ffn)(FrontParams) = SS == 2 ? k_front<2> : k_front<4>;
-            R4_LAUNCH(ffn, fgrid, kFrontWarps * 32, 0, s, fp);
+            size_t const fsm = (size_t)kFrontWarps * (SS == 2 ? FrontStage<2>::kBytes : FrontStage<4>::kBytes);
+            R4_LAUNCH(ffn, fgrid, kFrontWarps * 32, fsm, s, fp);
         }
         cudaEventRecord(after_front, s);
         unsigned grid = (n + kDetectWarps - 1) / kDetectWarps;

@@ -453,56 +453,52 @@ R4_HD int det_step(DetState &d, Levels const &lv, Trains const &t, int a, int f,
     }
     d.run += 1;
     int deferred = 0;
-    if (d.st == kPulse) {
-        if (below) {
-            if (d.run < kMinPulseSamples) {
-                if (d.ook_n <= 1) {
-                    d.st = kIdle;
+    if (d.st == kPulse || d.st == kGapStart) {
+        // the FSK sub-detector sees every sample of a first pulse and of the gap start behind it (:368-374, :414-420)
+        bool const feed = WithFsk && d.ook_n == 0;
+        if (d.st == kPulse) {
+            if (below) {
+                if (d.run < kMinPulseSamples) {
+                    if (d.ook_n <= 1) {
+                        d.st = kIdle;
+                    } else {
+                        d.eop_flag = 1;
+                        d.st = kGap;
+                    }
                 } else {
-                    d.eop_flag = 1;
-                    d.st = kGap;
+                    put(t.ook_pulse, d.ook_hw, d.ook_n, d.run);
+                    d.last_pulse = d.run;
+                    if (d.run > d.longest) d.longest = d.run;
+                    d.run = 0;
+                    d.st = kGapStart;
                 }
             } else {
-                put(t.ook_pulse, d.ook_hw, d.ook_n, d.run);
-                d.last_pulse = d.run;
-                if (d.run > d.longest) d.longest = d.run;
-                d.run = 0;
-                d.st = kGapStart;
+                d.high += a / 64 - d.high / 64;
+                if (d.high < lv.min_high) d.high = lv.min_high;
+                if (defer_f1 && d.ook_n != 0)
+                    deferred = kStepF1Deferred;
+                else
+                    d.ook_f1 += f / 64 - d.ook_f1 / 64;
             }
         } else {
-            d.high += a / 64 - d.high / 64;
-            if (d.high < lv.min_high) d.high = lv.min_high;
-            if (defer_f1 && d.ook_n != 0)
-                deferred = kStepF1Deferred;
-            else
-                d.ook_f1 += f / 64 - d.ook_f1 / 64;
+            if (above) {
+                d.run += d.last_pulse;
+                d.st = kPulse;
+            } else if (d.run >= kMinPulseSamples) {
+                d.st = kGap;
+                if (WithFsk && d.fsk_n > (unsigned)kMinPulses) { // only the first pulse feeds the FSK train: later gaps find fsk_n <= 16 (else the package ended here)
+                    close_fsk(d, t, fpdm);
+                    return 2;
+                }
+            }
         }
-        if (WithFsk && d.ook_n == 0) {
+        if (feed) {
             if (fpdm == 0)
                 fsk_classic(d, t, f, cx);
             else
                 fsk_minmax(d, t, f, cx);
         }
         return deferred;
-    }
-    if (d.st == kGapStart) {
-        if (above) {
-            d.run += d.last_pulse;
-            d.st = kPulse;
-        } else if (d.run >= kMinPulseSamples) {
-            d.st = kGap;
-            if (WithFsk && d.fsk_n > (unsigned)kMinPulses) { // only the first pulse feeds the FSK train: later gaps find fsk_n <= 16 (else the package ended here)
-                close_fsk(d, t, fpdm);
-                return 2;
-            }
-        }
-        if (WithFsk && d.ook_n == 0) {
-            if (fpdm == 0)
-                fsk_classic(d, t, f, cx);
-            else
-                fsk_minmax(d, t, f, cx);
-        }
-        return 0;
     }
     // kGap
     if (Mode == kStepFirst) return 0; // not reached: a first-pulse step is PULSE or GAP_START

@@ -39,8 +39,8 @@
 #include "r433b_core.cuh"
 #include "r433b_front.cuh"
 
-#ifndef R4_NO_PULSE0
-#define R4_NO_PULSE0 0
+#ifndef R4_REC
+#define R4_REC 2 // recurrence loop of burst_run: 0 always clamped, 1 clamp decided per 8 steps, 2 per stretch
 #endif
 namespace r433b {
 
@@ -194,7 +194,7 @@ __device__ __forceinline__ int fm_step(int y, long long a1, long long b0, int v,
 // n <= kFmWin, a a multiple of SPL; lane j of a batch takes the group at a + 32 * SPL * q + SPL * j.
 // With !fm_on the raw envelope goes straight to sm.fm instead.
 template <int SS>
-__device__ void disc_fill(FmJob const &jb, WarpSmem &sm, unsigned long long a, int n)
+__device__ R4_NOINLINE void disc_fill(FmJob const &jb, WarpSmem &sm, unsigned long long a, int n)
 {
     constexpr int SPL = 16 / SS;
     int const lane = threadIdx.x & 31;
@@ -777,11 +777,11 @@ __device__ R4_NOINLINE int idle_run(WarpSmem &sm, int n)
             int elo = lo, ehi = hi;
             if (act) {
                 if (elo == ehi) {
-#pragma unroll 4
+#pragma unroll 2
                     for (int k = k0; k < k1; ++k) elo += (int)chunk[k] > elo ? 1 : -1;
                     ehi = elo;
                 } else {
-#pragma unroll 4
+#pragma unroll 2
                     for (int k = k0; k < k1; ++k) {
                         int a = (int)chunk[k];
                         elo += a > elo ? 1 : -1;
@@ -838,6 +838,7 @@ __device__ R4_NOINLINE int idle_run(WarpSmem &sm, int n)
         __syncwarp();
         int q = d.low;
         int j = 0;
+#pragma unroll 1
         for (; j + 4 <= cnt; j += 4) {
             int4 const b = *reinterpret_cast<int4 const *>(&sm.q[j]);
             if (b.x > q) q += 2;
@@ -845,6 +846,7 @@ __device__ R4_NOINLINE int idle_run(WarpSmem &sm, int n)
             if (b.z > q) q += 2;
             if (b.w > q) q += 2;
         }
+#pragma unroll 1
         for (; j < cnt; ++j)
             if (sm.q[j] > q) q += 2;
         d.low = q - cnt;
@@ -920,8 +922,7 @@ __device__ R4_NOINLINE int burst_run(WarpSmem &sm, int n)
                 int const a = lane < cnt ? am_at(n + lane) : 32767;
                 int const aq = a >> 6; // am >= 0
                 int const top = __reduce_max_sync(0xffffffffu, lane < cnt ? aq : 0); // one REDUX each
-                int const bot = __reduce_min_sync(0xffffffffu, aq);
-                int hmax = 64 * top + 63;
+                    int hmax = 64 * top + 63;
                 hmax = h > hmax ? h : hmax;
                 unsigned const m = __ballot_sync(0xffffffffu, lane < cnt && a < det_thresholds(low, hmax, lv).down);
                 if (m) cnt = __ffs(m) - 1;
@@ -929,21 +930,57 @@ __device__ R4_NOINLINE int burst_run(WarpSmem &sm, int n)
                     __syncwarp();
                     sm.q[lane] = aq;
                     __syncwarp();
-                    int j = 0; // h >= min_high >= 0 here, so h / 64 == h >> 6
-                    if (64 * bot >= minh + 64) { // h - h/64 + q >= minh for every q >= bot when h >= minh: no clamp needed
-                        for (; j + 4 <= cnt; j += 4) {
-                            int4 const b = *reinterpret_cast<int4 const *>(&sm.q[j]);
-                            h += b.x - (int)((unsigned)h >> 6);
-                            h += b.y - (int)((unsigned)h >> 6);
-                            h += b.z - (int)((unsigned)h >> 6);
-                            h += b.w - (int)((unsigned)h >> 6);
-                        }
+                    // h >= min_high >= 0 here, so h / 64 == h >> 6.  Eight steps per trip, the loops kept rolled: seven
+                // warps per scheduler share an instruction cache of a few hundred instructions.
+                // q >= 0, so one step takes at most h >> 6 off, and less from a lower h: after k steps h is still
+                // >= h0 - k (h0 >> 6).  If that stays >= min_high over the whole stretch the clamp of :363 cannot act
+                // and is left out of the dependency chain.
+                int4 const *qp = reinterpret_cast<int4 const *>(sm.q);
+                int trips = cnt >> 3;
+#define R4_STEP(q) h += (q) - (int)((unsigned)h >> 6)
+#define R4_STEP_CLAMPED(q) h = max(h + (q) - (int)((unsigned)h >> 6), minh)
+#if R4_REC == 2
+                if (h - cnt * (int)((unsigned)h >> 6) >= minh) {
+#pragma unroll 1
+                    for (; trips > 0; --trips, qp += 2) {
+                        int4 const b = qp[0], c = qp[1];
+                        R4_STEP(b.x); R4_STEP(b.y); R4_STEP(b.z); R4_STEP(b.w);
+                        R4_STEP(c.x); R4_STEP(c.y); R4_STEP(c.z); R4_STEP(c.w);
                     }
-                    for (; j < cnt; ++j) {
-                        h += sm.q[j] - (int)((unsigned)h >> 6);
-                        h = h < minh ? minh : h;
+                } else {
+#pragma unroll 1
+                    for (; trips > 0; --trips, qp += 2) {
+                        int4 const b = qp[0], c = qp[1];
+                        R4_STEP_CLAMPED(b.x); R4_STEP_CLAMPED(b.y); R4_STEP_CLAMPED(b.z); R4_STEP_CLAMPED(b.w);
+                        R4_STEP_CLAMPED(c.x); R4_STEP_CLAMPED(c.y); R4_STEP_CLAMPED(c.z); R4_STEP_CLAMPED(c.w);
                     }
-                    log_add(L, log, rel, (unsigned)cnt, lane);
+                }
+#elif R4_REC == 1
+#pragma unroll 1
+                for (; trips > 0; --trips, qp += 2) {
+                    int4 const b = qp[0], c = qp[1];
+                    if (h - 8 * (int)((unsigned)h >> 6) >= minh) {
+                        R4_STEP(b.x); R4_STEP(b.y); R4_STEP(b.z); R4_STEP(b.w);
+                        R4_STEP(c.x); R4_STEP(c.y); R4_STEP(c.z); R4_STEP(c.w);
+                    } else {
+                        R4_STEP_CLAMPED(b.x); R4_STEP_CLAMPED(b.y); R4_STEP_CLAMPED(b.z); R4_STEP_CLAMPED(b.w);
+                        R4_STEP_CLAMPED(c.x); R4_STEP_CLAMPED(c.y); R4_STEP_CLAMPED(c.z); R4_STEP_CLAMPED(c.w);
+                    }
+                }
+#else
+#pragma unroll 1
+                for (; trips > 0; --trips, qp += 2) {
+                    int4 const b = qp[0], c = qp[1];
+                    R4_STEP_CLAMPED(b.x); R4_STEP_CLAMPED(b.y); R4_STEP_CLAMPED(b.z); R4_STEP_CLAMPED(b.w);
+                    R4_STEP_CLAMPED(c.x); R4_STEP_CLAMPED(c.y); R4_STEP_CLAMPED(c.z); R4_STEP_CLAMPED(c.w);
+                }
+#endif
+                {
+                    int const *qs = reinterpret_cast<int const *>(qp);
+#pragma unroll 1
+                    for (int r = cnt & 7; r > 0; --r, ++qs) h = max(h + *qs - (int)((unsigned)h >> 6), minh);
+                }
+                log_add(L, log, rel, (unsigned)cnt, lane);
                     run += cnt;
                     n += cnt;
                 }
@@ -1258,23 +1295,36 @@ __global__ void __launch_bounds__(kDetectWarps * 32, kDetectCtasPerSm) k_detect(
         int const nv_tile = remain < (unsigned long long)T ? (int)remain : T;
 
         // ---- AM tile from HBM ---------------------------------------------------------------------
+        // every load of the tile is issued before anything waits for one: the AM line of the lane's chunk, the
+        // chunk bounds, the two IQ samples of the hand-over check; the next tile is pulled into L2 meanwhile
         {
             uint4 const *g = reinterpret_cast<uint4 const *>(am_stream + t0 + (unsigned long long)(lane * C));
-            uint32_t *const mine = sm.am + lane * kAmStride;
-            uint4 v[4];
+            uint4 v[8];
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-#pragma unroll
-                for (int i = 0; i < 4; ++i) v[i] = g[4 * h + i];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    mine[16 * h + 4 * i + 0] = v[i].x;
-                    mine[16 * h + 4 * i + 1] = v[i].y;
-                    mine[16 * h + 4 * i + 2] = v[i].z;
-                    mine[16 * h + 4 * i + 3] = v[i].w;
+            for (int i = 0; i < 8; ++i) v[i] = g[i];
+            ChunkInfo const ci = chunk_stream[t0 / C + lane];
+            int x0 = 0, xm = 0;
+            if (t0 != 0) {
+                x0 = env_at<SS>(src, t0, p.flip, p.use_mag);
+                xm = env_at<SS>(src, t0 - 1, p.flip, p.use_mag);
+            }
+#ifndef R433B_SIMT_EMU
+            if (t0 + T < N) {
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<char const *>(g) + T * sizeof(int16_t)));
+                if (lane == 0) {
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(chunk_stream + (t0 + T) / C));
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(src + (t0 + T) * SS));
                 }
             }
-            ChunkInfo const ci = chunk_stream[t0 / C + lane];
+#endif
+            uint32_t *const mine = sm.am + lane * kAmStride;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                mine[4 * i + 0] = v[i].x;
+                mine[4 * i + 1] = v[i].y;
+                mine[4 * i + 2] = v[i].z;
+                mine[4 * i + 3] = v[i].w;
+            }
             bool const has = lane * C < nv_tile;
             sm.cmin[lane] = has ? (int)ci.cmin : 32767;
             sm.cmax[lane] = has ? (int)ci.cmax : 0;
@@ -1282,18 +1332,16 @@ __global__ void __launch_bounds__(kDetectWarps * 32, kDetectCtasPerSm) k_detect(
                 sm.ws.t0 = t0;
                 sm.ws.nv_tile = nv_tile;
             }
-        }
-        __syncwarp();
-        // hand-over check (see the file header): the first tile of a stream starts from the reset state in k_front
-        if (t0 != 0) {
-            int const x0 = env_at<SS>(src, t0, p.flip, p.use_mag);
-            int xm = env_at<SS>(src, t0 - 1, p.flip, p.use_mag);
-            // the reference keeps x[-1] as int16 across block calls (src/baseband.c:167)
-            if (t0 % p.block_samples == 0) xm = (int)(int16_t)xm;
-            int const expect = iir16_nowrap(y_am, a1, b0, x0 + xm);
-            if (expect != (int)(int16_t)am16[0]) {
-                am_repair<SS>(sm, src, t0, nv_tile, y_am, xm, a1, b0, p.flip, p.use_mag, am_stream + t0);
-                if (lane == 0) atomicAdd(&p.counters[5], 1u);
+            __syncwarp();
+            // hand-over check (see the file header): the first tile of a stream starts from the reset state in k_front
+            if (t0 != 0) {
+                // the reference keeps x[-1] as int16 across block calls (src/baseband.c:167)
+                if (t0 % p.block_samples == 0) xm = (int)(int16_t)xm;
+                int const expect = iir16_nowrap(y_am, a1, b0, x0 + xm);
+                if (expect != (int)(int16_t)am16[0]) {
+                    am_repair<SS>(sm, src, t0, nv_tile, y_am, xm, a1, b0, p.flip, p.use_mag, am_stream + t0);
+                    if (lane == 0) atomicAdd(&p.counters[5], 1u);
+                }
             }
         }
         y_am = am_tile_at(am16, nv_tile - 1);

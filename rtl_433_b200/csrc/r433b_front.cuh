@@ -35,7 +35,10 @@ namespace r433b {
 
 constexpr int kChunk = 64;                 // samples per lane per tile
 constexpr int kTile = 32 * kChunk;         // 2048
-constexpr int kWarmAm = 64;                // warm-up samples of the AM trajectory (multiple of 16, <= kChunk)
+#ifndef R4_WARM_AM
+#define R4_WARM_AM 64
+#endif
+constexpr int kWarmAm = R4_WARM_AM;                // warm-up samples of the AM trajectory (multiple of 16, <= kChunk)
 constexpr int kFrontWarps = 4;             // warps (tiles) per CTA of k_front
 constexpr int kFrontCtasPerSm = 12;
 
@@ -120,7 +123,8 @@ __device__ __forceinline__ int env_at(uint8_t const *src, unsigned long long pos
 {
     uint8_t const *g = src + pos * SS;
     if (SS == 2) {
-        int i = (int)(g[0] ^ (flip & 0xff)), q = (int)(g[1] ^ (flip & 0xff));
+        unsigned const w = (unsigned)*reinterpret_cast<uint16_t const *>(g) ^ (flip & 0xffff); // streams start 16-byte aligned
+        int i = (int)(w & 0xff), q = (int)(w >> 8);
         return use_mag ? mag_cu8(i, q) : env_cu8(i, q);
     }
     uint32_t w = *reinterpret_cast<uint32_t const *>(g) ^ flip;
@@ -145,11 +149,44 @@ struct FrontParams {
     int spoil;                            // tests: 1 = lane 0's guess is made wrong, 2 = every lane's (R433B_SPOIL_FRONT)
 };
 
+// Shared-memory staging of one tile's IQ: the chunks [-kWarmChunks, 32) of the tile, every chunk (C samples)
+// followed by 16 bytes of padding so that the lanes' 128-bit reads of their own chunks spread over all banks.
+constexpr int kWarmChunks = (kWarmAm + kChunk - 1) / kChunk;
+template <int SS>
+struct FrontStage {
+    static constexpr int kChunkBytes = kChunk * SS;
+    static constexpr int kSlot = kChunkBytes + 16;
+    static constexpr int kPieces = (32 + kWarmChunks) * (kChunkBytes / 16); // 16-byte pieces per tile
+    static constexpr int kBytes = (32 + kWarmChunks) * kSlot;
+    // byte offset in the stage of sample `rel` (relative to the tile start, >= -kWarmChunks * C), a multiple of 16 / SS
+    static __device__ __forceinline__ int at(int rel) { return ((rel + kWarmChunks * kChunk) / kChunk) * kSlot + ((rel + kWarmChunks * kChunk) % kChunk) * SS; }
+};
+
+// 16 bytes global -> shared, asynchronously; bytes past `valid` (0..16) are zero-filled
+__device__ __forceinline__ void stage_piece(void *dst_smem, void const *src, int valid)
+{
+#ifdef R433B_SIMT_EMU
+    uint8_t *d = reinterpret_cast<uint8_t *>(dst_smem);
+    for (int i = 0; i < 16; ++i) d[i] = i < valid ? reinterpret_cast<uint8_t const *>(src)[i] : 0;
+#else
+    unsigned const d = (unsigned)__cvta_generic_to_shared(dst_smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(valid) : "memory");
+#endif
+}
+__device__ __forceinline__ void stage_wait()
+{
+#ifndef R433B_SIMT_EMU
+    asm volatile("cp.async.wait_all;" ::: "memory");
+#endif
+}
+
 template <int SS>
 __global__ void __launch_bounds__(kFrontWarps * 32, kFrontCtasPerSm) k_front(FrontParams p)
 {
     constexpr int SPL = 16 / SS;
     constexpr int C = kChunk;
+    using St = FrontStage<SS>;
+    R4_DYN_SMEM(uint8_t, front_smem);
     int const lane = threadIdx.x & 31;
     unsigned long long const w = (unsigned long long)blockIdx.x * kFrontWarps + (threadIdx.x >> 5);
     unsigned const s = (unsigned)(w / p.tiles);
@@ -162,6 +199,31 @@ __global__ void __launch_bounds__(kFrontWarps * 32, kFrontCtasPerSm) k_front(Fro
     unsigned long long const remain = N - t0;
     int const nv_tile = remain < (unsigned long long)kTile ? (int)remain : kTile;
     int const a1 = p.a1, b0 = p.b0;
+    uint8_t *const stage = front_smem + (threadIdx.x >> 5) * St::kBytes;
+
+    // ---- the tile's IQ (and the warm-up samples in front of it) into shared memory: coalesced 16-byte pieces,
+    //      all of them in flight at once; nothing in front of the stream or past its end is touched ----
+    {
+        long long const first = (long long)t0 - kWarmChunks * C; // sample of piece 0
+#pragma unroll 1
+        for (int i = lane; i < St::kPieces; i += 32) {
+            long long const smp = first + (long long)i * SPL;
+            long long const left = (long long)N - smp; // samples of the stream from smp on
+            int const valid = smp < 0 ? 0 : (left >= SPL ? 16 : (left > 0 ? (int)left * SS : 0));
+            int const piece_in_chunk = i % (St::kChunkBytes / 16);
+            int const chunk = i / (St::kChunkBytes / 16);
+            stage_piece(stage + chunk * St::kSlot + piece_in_chunk * 16, valid ? src + smp * SS : src, valid);
+        }
+        stage_wait();
+        __syncwarp();
+    }
+    auto group_at = [&](int rel, uint32_t (&rw)[4]) { // the SPL samples from tile sample `rel` on (a multiple of SPL)
+        uint4 const v = *reinterpret_cast<uint4 const *>(stage + St::at(rel));
+        rw[0] = v.x ^ p.flip;
+        rw[1] = v.y ^ p.flip;
+        rw[2] = v.z ^ p.flip;
+        rw[3] = v.w ^ p.flip;
+    };
 
     int const base = lane * C;
     int nv = nv_tile - base;
@@ -173,17 +235,20 @@ __global__ void __launch_bounds__(kFrontWarps * 32, kFrontCtasPerSm) k_front(Fro
     if (gpos != 0 && nv > 0) {
         uint32_t rw[4];
         int x[SPL];
-        if (gpos >= (unsigned long long)(kWarmAm + SPL)) {
+        int g0 = -kWarmAm; // warm-up start relative to the chunk
+        if (gpos >= (unsigned long long)kWarmAm) {
             // guess: the filter has (almost) unit gain, its state is near the local envelope
-            load_group<SS>(src, gpos - kWarmAm - SPL, SPL, p.flip, rw);
+            group_at(base - kWarmAm, rw);
             env_group<SS>(rw, p.use_mag, x);
-            xp = x[SPL - 1];
-            y = (x[SPL - 1] + x[SPL - 2]) >> 1;
+            xp = x[0];
+            y = (x[0] + x[1]) >> 1;
             if (y > 32767) y = 32767;
-        } // else the warm-up begins at sample 0 of the stream: the reset state, exact
+        } else {
+            g0 = -(int)gpos; // the warm-up begins at sample 0 of the stream: the reset state, exact
+        }
 #pragma unroll 2
-        for (int g = -kWarmAm; g < 0; g += SPL) {
-            load_group<SS>(src, gpos + g, SPL, p.flip, rw);
+        for (int g = g0; g < 0; g += SPL) {
+            group_at(base + g, rw);
             env_group<SS>(rw, p.use_mag, x);
             // (a block start inside the warm-up is not modelled: the state is a guess anyway)
 #pragma unroll
@@ -212,7 +277,7 @@ __global__ void __launch_bounds__(kFrontWarps * 32, kFrontCtasPerSm) k_front(Fro
                 uint32_t rw[4];
                 int x[SPL];
                 uint32_t o[SPL / 2];
-                load_group<SS>(src, gpos + k, SPL, p.flip, rw);
+                group_at(base + k, rw);
                 env_group<SS>(rw, p.use_mag, x);
 #pragma unroll
                 for (int j = 0; j < SPL; j += 2) {
@@ -238,17 +303,20 @@ __global__ void __launch_bounds__(kFrontWarps * 32, kFrontCtasPerSm) k_front(Fro
                     *reinterpret_cast<uint2 *>(out + k) = v;
                 }
             }
-            if (k < nv) { // ragged end of the stream
+            if (k < nv) { // ragged end of the stream (the stage is zero-filled past it)
                 uint32_t rw[4];
                 int x[SPL];
-                load_group<SS>(src, gpos + k, nv - k, p.flip, rw);
+                group_at(base + k, rw);
                 env_group<SS>(rw, p.use_mag, x);
-                for (int j = 0; k + j < nv; ++j) {
-                    yy = iir16_nowrap(yy, a1, b0, x[j] + xx);
-                    xx = x[j];
-                    cmin = min(cmin, yy);
-                    cmax = max(cmax, yy);
-                    out[k + j] = (int16_t)yy;
+#pragma unroll
+                for (int j = 0; j < SPL; ++j) {
+                    if (k + j < nv) {
+                        yy = iir16_nowrap(yy, a1, b0, x[j] + xx);
+                        xx = x[j];
+                        cmin = min(cmin, yy);
+                        cmax = max(cmax, yy);
+                        out[k + j] = (int16_t)yy;
+                    }
                 }
             }
             y_end = yy;

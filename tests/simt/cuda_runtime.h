@@ -88,4 +88,4 @@ inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t = nullptr) { return
 inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
 inline cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t, cudaEvent_t) { *ms = 0.0f; return cudaSuccess; }
 inline cudaError_t cudaFuncSetAttribute(void const *, int, int) { return cudaSuccess; }
-enum { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
+enum { cudaFuncAttributeMaxDynamicSharedMemorySize = 8, cudaFuncAttributePreferredSharedMemoryCarveout = 9 };
