@@ -5,6 +5,7 @@ import csv
 import io
 import json
 import subprocess
+import os
 import sys
 import os as _os
 KF = ["-k", "regex:" + _os.environ["NCU_KERNEL"]] if _os.environ.get("NCU_KERNEL") else []
@@ -45,9 +46,15 @@ rd, wr, dur = num("dram__bytes_read.sum"), num("dram__bytes_write.sum"), num("gp
 lines += ["", f"DRAM traffic per launch: {rd / 1e9:.3f} GB read + {wr / 1e9:.3f} GB written = {(rd + wr) / 1e9:.3f} GB in {dur * 1e3:.2f} ms "
           f"(under the profiler) = {(rd + wr) / dur / 1e9:.1f} GB/s"]
 if traffic_json:
-    json.dump({"kernel": kernel, "dram_bytes_per_launch": int(rd + wr), "dram_bytes_read": int(rd), "dram_bytes_write": int(wr),
-               "workload": "4096 x 2^20-sample cu8 streams (tools/quick_perf.py --streams 4096 --distinct 32)", "report": rep},
-              open(traffic_json, "w"), indent=1)
+    short = "k_front" if "k_front" in kernel else "k_detect" if "k_detect" in kernel else "k_slice" if "k_slice" in kernel else kernel
+    wl = os.environ.get("NCU_WORKLOAD", "ook_cu8_250k")
+    try:
+        allt = json.load(open(traffic_json))
+    except Exception:
+        allt = {}
+    allt.setdefault(wl, {})[short] = {"dram_bytes_per_launch": int(rd + wr), "dram_bytes_read": int(rd), "dram_bytes_write": int(wr),
+                                       "duration_ms_under_profiler": round(dur * 1e3, 3), "report": os.path.basename(rep)}
+    json.dump(allt, open(traffic_json, "w"), indent=1, sort_keys=True)
 src = subprocess.run(["ncu", "-i", rep] + KF + [ "--page", "source", "--print-source", "cuda,sass", "--csv"], capture_output=True, text=True).stdout
 cur, hd, agg = None, None, collections.OrderedDict()
 for r in csv.reader(io.StringIO(src)):
@@ -89,7 +96,10 @@ def source_text(fn, ln):
 
 for (fn, ln), (sm, ins, text) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:25]:
     lines.append(f"| {100 * sm / ts:.1f}% | {100 * ins / ti:.1f}% | {fn}:{ln} | `{source_text(fn, ln)}` |")
-kind = "detect" if "k_detect" in kernel else "slice" if "k_slice" in kernel else None
+if "k_detect" in kernel:
+    fn = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_funcs.py"), rep, "k_detectILi2"], capture_output=True, text=True).stdout
+    lines += ["", "## by device function (tools/ncu_funcs.py; the phases of the walk are separate functions)", "", fn.rstrip()]
+kind = "slice" if "k_slice" in kernel else None
 if kind:
     reg = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_regions.py"), rep, kind], capture_output=True, text=True).stdout
     lines += ["", "## by code region (tools/ncu_regions.py; IQ samples of the 4096 x 2^20 workload)", "", reg.rstrip()]
