@@ -236,8 +236,8 @@ R4_HD_COLD void fsk_shift_move(int *pulse, int *gap, Ctx cx)
     }
     cx.sync();
 }
-template <class Ctx>
-R4_HD void fsk_shift(DetState &d, Trains const &t, Ctx &cx)
+template <class D, class Ctx>
+R4_HD void fsk_shift(D &d, Trains const &t, Ctx &cx)
 {
     fsk_shift_move(t.fsk_pulse, t.fsk_gap, cx);
     d.fsk_n -= kMaxPulses / 2;
@@ -246,8 +246,8 @@ R4_HD void fsk_shift(DetState &d, Trains const &t, Ctx &cx)
 }
 
 // src/pulse_detect_fsk.c:34-141
-template <class Ctx>
-R4_HD void fsk_classic(DetState &d, Trains const &t, int v, Ctx &cx)
+template <class D, class Ctx>
+R4_HD void fsk_classic(D &d, Trains const &t, int v, Ctx &cx)
 {
     int d1 = v - d.fk_f1, d2 = v - d.fk_f2;
     d1 = d1 < 0 ? -d1 : d1;
@@ -326,8 +326,8 @@ R4_HD void fsk_wrap_up(DetState &d, Trains const &t)
 }
 
 // src/pulse_detect_fsk.c:158-221 (int16 trackers; f1/f2 deliberately crossed, :192/:208)
-template <class Ctx>
-R4_HD void fsk_minmax(DetState &d, Trains const &t, int v, Ctx &cx)
+template <class D, class Ctx>
+R4_HD void fsk_minmax(D &d, Trains const &t, int v, Ctx &cx)
 {
     if (d.fk_skip == 0) {
         if (v > d.fk_vmax) d.fk_vmax = v;

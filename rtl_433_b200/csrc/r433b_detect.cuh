@@ -1085,6 +1085,91 @@ __device__ R4_NOINLINE int burst_run(WarpSmem &sm, int n)
     return n;
 }
 
+// The FIRST pulse of a package, from tile sample n on (src/pulse_detect.c:355-374 with ook_n == 0): the high-level
+// estimator, the carrier estimate (not yet deferred) and the FSK sub-detector are fed sample by sample -- an FSK
+// transmission is one long OOK "pulse", so this is the hot loop of FSK captures.  The same bound as in
+// burst_run() tells which samples cannot end the pulse; the first one that might is left to the generic step.
+// Reads FM: windows are made current as the walk reaches them.  Returns the first sample not consumed.
+template <int SS>
+__device__ R4_NOINLINE int first_run(WarpSmem &sm, int n)
+{
+    int const lane = threadIdx.x & 31;
+    uint16_t const *am16 = reinterpret_cast<uint16_t const *>(sm.am);
+    __syncwarp();
+    struct {
+        int high, run, ook_f1;
+        unsigned fsk_n, fsk_hw;
+        unsigned long long fsk_offset;
+        unsigned fk_len;
+        int fk_st, fk_f1, fk_f2, fk_vmax, fk_vmin, fk_skip;
+    } d = {sm.ws.d.high, sm.ws.d.run, sm.ws.d.ook_f1, sm.ws.d.fsk_n, sm.ws.d.fsk_hw, sm.ws.d.fsk_offset, sm.ws.d.fk_len,
+           sm.ws.d.fk_st, sm.ws.d.fk_f1, sm.ws.d.fk_f2, sm.ws.d.fk_vmax, sm.ws.d.fk_vmin, sm.ws.d.fk_skip};
+    int const low = sm.ws.d.low;
+    Levels const lv = sm.wc.lv;
+    Trains const tr = sm.wc.tr;
+    int const fpdm = sm.wc.fpdm, minh = lv.min_high;
+    bool const lazy_fm = sm.wc.lazy_fm != 0;
+    int const nv_tile = sm.ws.nv_tile;
+    unsigned long long const t0 = sm.ws.t0;
+    WarpCtx cx;
+    cx.lane = lane;
+    cx.nlanes = 32;
+#pragma unroll 1
+    while (n < nv_tile) {
+        unsigned long long const pos = t0 + (unsigned long long)n;
+        if (!(sm.win_n > 0 && pos >= sm.win0 && pos < sm.win0 + (unsigned long long)sm.win_n))
+            fm_for_walk<SS>(sm.wc.jb, sm, pos, t0, nv_tile, lazy_fm);
+        int cnt = nv_tile - n < 32 ? nv_tile - n : 32;
+        int const in_win = (int)(sm.win0 + (unsigned long long)sm.win_n - pos);
+        cnt = cnt < in_win ? cnt : in_win;
+        int const a = lane < cnt ? am_tile_at(am16, n + lane) : 32767;
+        int const f = lane < cnt ? (int)(int16_t)sm.fm[fm_pidx((int)(pos - sm.win0) + lane)] : 0;
+        int const aq = a >> 6;
+        int const top = __reduce_max_sync(0xffffffffu, lane < cnt ? aq : 0);
+        int hmax = 64 * top + 63;
+        hmax = d.high > hmax ? d.high : hmax;
+        unsigned const m = __ballot_sync(0xffffffffu, lane < cnt && a < det_thresholds(low, hmax, lv).down);
+        if (m) cnt = __ffs(m) - 1;
+        if (cnt) {
+            __syncwarp();
+            sm.q[lane] = (aq << 16) | (f & 0xffff); // one word per sample: am / 64 above, FM below
+            __syncwarp();
+#pragma unroll 1
+            for (int j = 0; j < cnt; ++j) {
+                int const w = sm.q[j];
+                int const fj = (int)(int16_t)(w & 0xffff);
+                d.high = max(d.high + (w >> 16) - (int)((unsigned)d.high >> 6), minh);
+                d.ook_f1 += fj / 64 - d.ook_f1 / 64;
+                if (fpdm == 0)
+                    fsk_classic(d, tr, fj, cx);
+                else
+                    fsk_minmax(d, tr, fj, cx);
+            }
+            d.run += cnt;
+            n += cnt;
+        }
+        if (m) break; // this sample might end the pulse: the generic step tests it exactly
+    }
+    __syncwarp();
+    if (lane == 0) {
+        sm.ws.d.high = d.high;
+        sm.ws.d.run = d.run;
+        sm.ws.d.ook_f1 = d.ook_f1;
+        sm.ws.d.fsk_n = d.fsk_n;
+        sm.ws.d.fsk_hw = d.fsk_hw;
+        sm.ws.d.fsk_offset = d.fsk_offset;
+        sm.ws.d.fk_len = d.fk_len;
+        sm.ws.d.fk_st = d.fk_st;
+        sm.ws.d.fk_f1 = d.fk_f1;
+        sm.ws.d.fk_f2 = d.fk_f2;
+        sm.ws.d.fk_vmax = d.fk_vmax;
+        sm.ws.d.fk_vmin = d.fk_vmin;
+        sm.ws.d.fk_skip = d.fk_skip;
+    }
+    __syncwarp();
+    return n;
+}
+
 // Everything else, one sample (or one stretch of a first pulse) at a time: package starts, first pulses with
 // the FSK sub-detector (they read FM), spurious pulses, the 1200th pulse, filters that rule the deferred
 // estimate out.  Always makes progress: it consumes at least one sample or hands a package over (ws.pend_type).
@@ -1134,48 +1219,12 @@ __device__ R4_NOINLINE int generic_step(WarpSmem &sm, int n)
     };
     auto fm_at = [&](int i) -> int { return (int)(int16_t)sm.fm[fm_pidx((int)(t0 + (unsigned long long)i - sm.win0))]; };
 
-    // PULSE of the FIRST pulse: the same bound, with the FSK sub-detector and the (not yet deferred)
-    // carrier estimate fed in the loop (src/pulse_detect.c:362-371).  An FSK transmission is one long OOK
-    // "pulse", so this is the hot loop of FSK captures.  Needs FM: stays inside the current window.
-    auto pulse0_fast = [&](int n) -> int {
-        int cnt = nv_tile - n < 32 ? nv_tile - n : 32;
-        int const in_win = (int)(sm.win0 + (unsigned long long)sm.win_n - (t0 + (unsigned long long)n));
-        cnt = cnt < in_win ? cnt : in_win;
-        int a = lane < cnt ? am_at(n + lane) : 32767;
-        int f = lane < cnt ? fm_at(n + lane) : 0;
-        int aq = a >> 6;
-        int const top = __reduce_max_sync(0xffffffffu, lane < cnt ? aq : 0);
-        int hmax = 64 * top + 63;
-        hmax = d.high > hmax ? d.high : hmax;
-        Thresholds th = det_thresholds(d.low, hmax, lv);
-        unsigned m = __ballot_sync(0xffffffffu, lane < cnt && a < th.down);
-        if (m) cnt = __ffs(m) - 1;
-        if (cnt == 0) return 0;
-        int const minh = lv.min_high;
-#pragma unroll 1
-        for (int j = 0; j < cnt; ++j) {
-            int aj = __shfl_sync(0xffffffffu, aq, j);
-            int fj = __shfl_sync(0xffffffffu, f, j);
-            d.high += aj - (int)((unsigned)d.high >> 6);
-            d.high = d.high < minh ? minh : d.high;
-            d.ook_f1 += fj / 64 - d.ook_f1 / 64;
-            if (fpdm == 0)
-                fsk_classic(d, tr, fj, cx);
-            else
-                fsk_minmax(d, tr, fj, cx);
-        }
-        d.run += cnt;
-        return cnt;
-    };
-
-
     // inside a first pulse (and its GAP_START) the FSK sub-detector and the undeferred estimate read FM
     bool const first = d.ook_n == 0 && (d.st == kPulse || d.st == kGapStart);
     bool const wants_fm = first || (d.st == kPulse && !defer_f1);
     if (wants_fm) fm_need(n);
     int adv = 0;
-    if (first && d.st == kPulse) adv = pulse0_fast(n);
-    if (!adv) {
+    {
         // every lane runs the (warp-uniform) step and writes the same train entries: keep the lanes
         // together so that no lane reads an entry another lane has already overwritten for a later sample
         __syncwarp();
@@ -1373,6 +1422,8 @@ __global__ void __launch_bounds__(kDetectWarps * 32, kDetectCtasPerSm) k_detect(
                 m = idle_run(sm, n);
             else if (defer_f1 && !sm.ws.d.eop_flag && (sm.ws.d.ook_n != 0 || st == kGap))
                 m = burst_run(sm, n);
+            else if (st == kPulse && sm.ws.d.ook_n == 0)
+                m = first_run<SS>(sm, n);
             if (m == n && !sm.ws.pend_type) m = generic_step<SS>(sm, n);
             n = m;
             if (sm.ws.pend_type) { // a package to hand over; the sample at n is looked at again

@@ -3,6 +3,9 @@ registered inside oracle/_ref) are driven by the product's r433b_dispatch_r_devi
 results; decoded JSON and every decoder's decode_events/ok/messages/fails counters must equal a
 pure-reference run of the same capture (real decoders chained, so priority gating is live)."""
 import ctypes as C
+import json
+import os
+import subprocess
 
 import numpy as np
 import pytest
@@ -39,3 +42,31 @@ def test_reference_decoders_behind_gpu_path():
     assert got_stats == want_stats
     assert sum(s[0] for s in got_stats) > 1000  # thousands of decode_fn calls took place
     ctx.close()
+
+
+SHIM = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "shim_c99")
+
+
+@pytest.mark.skipif(not os.path.exists(SHIM), reason="oracle/_ref/shim_c99 not built/shipped (make -C oracle shim)")
+def test_c99_shim_of_integration_md(tmp_path):
+    """INTEGRATION.md section 2, compiled verbatim as C99 against the reference's headers and linked with the
+    reference's unmodified objects + libr433b.so (oracle/Makefile `shim`): the reference's decoders, its
+    data_acquired_handler and its JSON printer run behind the GPU path.  Two capture files in one batch; the
+    messages must be the ones a pure-reference run decodes, in order."""
+    files = [synth.silvercrest_file(),
+             synth.ook_stream(5, n_samples=1 << 19, n_bursts=4, kinds=("silvercrest", "nexus", "nice"), decodable=True)]
+    want = []
+    r = refh.Ref(chain_decoders=True, store_bitbuffers=False)
+    r.register_defaults()
+    for x in files:
+        want += [json.loads(l) for l in r.run(x, 2)["json"] if l]
+    assert any(m.get("model") == "Silvercrest-Remote" for m in want)
+    paths = []
+    for i, x in enumerate(files):
+        p = tmp_path / f"g{i:03d}_433.92M_250k.cu8"
+        x.tofile(p)
+        paths.append(str(p))
+    out = subprocess.run([SHIM, "250000"] + paths, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    got = [json.loads(l) for l in out.stdout.split("\n") if l.strip()]
+    assert got == want
