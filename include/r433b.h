@@ -182,6 +182,38 @@ int r433b_dispatch(r433b_ctx *ctx, r433b_results const *res, uint32_t stream, r4
 int r433b_dispatch_r_devices(r433b_ctx *ctx, r433b_results const *res, uint32_t stream,
         struct r_device *const *devs, uint32_t n);
 
+/* ---- pulse-level I/O: packages that never were IQ --------------------------------------
+   `rtl_433 -r file.ook` (src/rtl_433.c:1755-1790) and RfRaw test data (-y, src/rtl_433.c:1620-1650) skip the
+   demodulator and hand loaded pulse_data_t to run_ook_demods() / run_fsk_demods().  Here the loaded packages
+   go to the slicer kernel; fetch / dispatch / digest work as after r433b_process().  The text formats are
+   read and written on the host (no GPU needed for r433b_pulses_* and r433b_format_*). */
+typedef struct r433b_pulses r433b_pulses; /* a growable set of packages, each tagged with a stream (file) index */
+r433b_pulses *r433b_pulses_create(void);
+void r433b_pulses_destroy(r433b_pulses *ps);
+void r433b_pulses_clear(r433b_pulses *ps);
+/* pulse_data_load() (src/pulse_data.c:123-181) until the text is exhausted; samp_rate = cfg->samp_rate.
+   Returns the number of packages appended (>= 0) or a negative error. */
+int r433b_pulses_load_ook(r433b_pulses *ps, uint32_t stream, char const *text, size_t len, uint32_t samp_rate);
+/* rfraw_check() + rfraw_parse() (src/rfraw.c:67-206) of one line into a zeroed pulse_data_t: 1 package, or 0 if the
+   line is not RfRaw */
+int r433b_pulses_load_rfraw(r433b_pulses *ps, uint32_t stream, char const *line);
+/* a caller-built pulse_data_t (fsk_f2_est != 0 selects run_fsk_demods, as in the reference) */
+int r433b_pulses_add(r433b_pulses *ps, uint32_t stream, struct pulse_data const *pd);
+uint32_t r433b_pulses_count(r433b_pulses const *ps);
+int r433b_pulses_get(r433b_pulses const *ps, uint32_t index, struct pulse_data *out);
+/* All slicers of the registered devices on every package of the set (k_slice only). */
+int r433b_process_pulses(r433b_ctx *ctx, r433b_pulses const *ps);
+
+/* Writers; all return the length of the full text (snprintf convention), writing at most cap bytes.
+   pulse_data_dump() src/pulse_data.c:193-226 (`received` = text after ";received ", NULL leaves the line out);
+   pulse_data_print_pulse_header() :183-191; pulse_data_print_vcd() :102-121 (ch_id '\'' = AM/OOK, '"' = FM/FSK);
+   pulse_data_print_vcd_header() :78-100; pulse_data_dump_raw() :58-68 (logic.u8: 0x02 OOK, 0x04 FSK). */
+size_t r433b_format_ook(struct pulse_data const *pd, char const *received, char *buf, size_t cap);
+size_t r433b_format_ook_header(char const *created, char *buf, size_t cap);
+size_t r433b_format_vcd(struct pulse_data const *pd, int ch_id, char *buf, size_t cap);
+size_t r433b_format_vcd_header(uint32_t sample_rate, char const *date, char *buf, size_t cap);
+void r433b_dump_logic_u8(uint8_t *buf, uint64_t len, uint64_t buf_offset, struct pulse_data const *pd, uint8_t bits);
+
 #ifdef __cplusplus
 }
 #endif

@@ -649,3 +649,84 @@ REFH_EXPORT void refh_parse_filename(char const *name, uint32_t out[3])
     out[1] = info.sample_rate;
     out[2] = info.center_frequency;
 }
+
+/* -------- pulse-level I/O of the reference (src/pulse_data.c, src/rfraw.c), SURVEY 8(f4) -------- */
+#include "rfraw.h"
+
+/* pulse_data_load() until a package comes back empty (the .ook loop of src/rtl_433.c:1755-1760); the loaded
+   pulse_data_t are stored back to back in `out` (cap entries).  Returns the number loaded. */
+REFH_EXPORT int refh_load_ook(char const *text, size_t len, uint32_t samp_rate, pulse_data_t *out, int cap)
+{
+    FILE *f = fmemopen((void *)text, len, "r");
+    if (!f) return -1;
+    struct timeval now = {0, 0};
+    r_logger_set_log_handler(quiet_log, NULL);
+    int n = 0;
+    while (n < cap) {
+        pulse_data_load(f, &now, &out[n], samp_rate);
+        if (!out[n].num_pulses) break;
+        n++;
+    }
+    fclose(f);
+    return n;
+}
+
+REFH_EXPORT int refh_rfraw(char const *line, pulse_data_t *out)
+{
+    memset(out, 0, sizeof(*out));
+    if (!rfraw_check(line)) return 0;
+    rfraw_parse(out, line);
+    return 1;
+}
+
+/* pulse_data_dump() / pulse_data_print_vcd() / pulse_data_dump_raw() output into a caller buffer */
+REFH_EXPORT size_t refh_dump_ook(pulse_data_t const *pd, char *buf, size_t cap)
+{
+    char *mem = NULL;
+    size_t n = 0;
+    FILE *f = open_memstream(&mem, &n);
+    pulse_data_dump(f, pd);
+    fclose(f);
+    if (n < cap) memcpy(buf, mem, n + 1);
+    free(mem);
+    return n;
+}
+
+REFH_EXPORT size_t refh_dump_vcd(pulse_data_t const *pd, int ch_id, int with_header, char *buf, size_t cap)
+{
+    char *mem = NULL;
+    size_t n = 0;
+    FILE *f = open_memstream(&mem, &n);
+    if (with_header) pulse_data_print_vcd_header(f, pd->sample_rate);
+    pulse_data_print_vcd(f, pd, ch_id);
+    fclose(f);
+    if (n < cap) memcpy(buf, mem, n + 1);
+    free(mem);
+    return n;
+}
+
+REFH_EXPORT void refh_dump_raw(uint8_t *buf, unsigned len, uint64_t buf_offset, pulse_data_t const *pd, uint8_t bits)
+{
+    pulse_data_dump_raw(buf, len, buf_offset, pd, bits);
+}
+
+/* run_ook_demods() / run_fsk_demods() (by fsk_f2_est, src/rtl_433.c:1774-1778) over all registered devices on a
+   loaded pulse_data_t; events are captured like those of refh_run_stream() */
+REFH_EXPORT int refh_slice_pulse_data(refh_t *h, pulse_data_t *pd)
+{
+    clear_results(h);
+    g_active = h;
+    h->pkgs = grow(h->pkgs, &h->cap_pkgs, 1, sizeof(*h->pkgs));
+    memset(&h->pkgs[0], 0, sizeof(h->pkgs[0]));
+    h->n_pkgs = 1;
+    list_t all = {0};
+    list_ensure_size(&all, (size_t)h->n_devs + 1);
+    for (int i = 0; i < h->n_devs; ++i) list_push(&all, h->devs[i]);
+    if (pd->fsk_f2_est)
+        run_fsk_demods(&all, pd);
+    else
+        run_ook_demods(&all, pd);
+    free(all.elems);
+    g_active = NULL;
+    return (int)h->n_evts;
+}

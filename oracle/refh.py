@@ -112,6 +112,14 @@ def lib():
         L.refh_magnitude_est_cs16.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
         L.refh_low_pass.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]
         L.refh_demod_fm.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_ulong, C.c_uint32, C.c_float, C.c_void_p]
+        L.refh_load_ook.argtypes = [C.c_char_p, C.c_size_t, C.c_uint32, C.c_void_p, C.c_int]
+        L.refh_rfraw.argtypes = [C.c_char_p, C.c_void_p]
+        L.refh_dump_ook.restype = C.c_size_t
+        L.refh_dump_ook.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t]
+        L.refh_dump_vcd.restype = C.c_size_t
+        L.refh_dump_vcd.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_char_p, C.c_size_t]
+        L.refh_dump_raw.argtypes = [C.c_void_p, C.c_uint, C.c_uint64, C.c_void_p, C.c_uint8]
+        L.refh_slice_pulse_data.argtypes = [C.c_void_p, C.c_void_p]
         _lib = L
     return _lib
 
@@ -268,3 +276,70 @@ def row_hex(bb, row):
     data = bytes(bb["bb"][row][:nbytes]) if nbytes <= BITBUF_COLS else bytes(bb["bb"].reshape(-1)[row * BITBUF_COLS:row * BITBUF_COLS + nbytes])
     hx = data.hex()
     return "{%d}%s" % (n, hx[:(n + 3) // 4])
+
+
+# ---- pulse-level I/O of the reference (src/pulse_data.c, src/rfraw.c) ------------------------------------
+
+PULSE_DATA_DTYPE = np.dtype([("offset", "<u8"), ("sample_rate", "<u4"), ("depth_bits", "<u4"), ("start_ago", "<u4"),
+                             ("end_ago", "<u4"), ("num_pulses", "<u4"), ("pulse", "<i4", (1200,)), ("gap", "<i4", (1200,)),
+                             ("ook_low_estimate", "<i4"), ("ook_high_estimate", "<i4"), ("fsk_f1_est", "<i4"),
+                             ("fsk_f2_est", "<i4"), ("freq1_hz", "<f4"), ("freq2_hz", "<f4"), ("centerfreq_hz", "<f4"),
+                             ("range_db", "<f4"), ("rssi_db", "<f4"), ("snr_db", "<f4"), ("noise_db", "<f4")], align=True)
+assert PULSE_DATA_DTYPE.itemsize == 9672
+
+
+def load_ook(text, samp_rate, cap=64):
+    """pulse_data_load() until exhausted -> array of pulse_data_t records."""
+    if isinstance(text, str):
+        text = text.encode()
+    out = np.zeros(cap + 1, PULSE_DATA_DTYPE)
+    n = lib().refh_load_ook(text, len(text), samp_rate, out.ctypes.data, cap)
+    assert n >= 0
+    return out[:n].copy()
+
+
+def rfraw(line):
+    """rfraw_check() + rfraw_parse() into a zeroed pulse_data_t -> record or None."""
+    out = np.zeros(1, PULSE_DATA_DTYPE)
+    if not lib().refh_rfraw(line.encode() if isinstance(line, str) else line, out.ctypes.data):
+        return None
+    return out[0]
+
+
+def dump_ook(pd):
+    """pulse_data_dump() text (with its ';received <wall clock>' first line)."""
+    pd = np.ascontiguousarray(pd)
+    buf = C.create_string_buffer(1 << 16)
+    n = lib().refh_dump_ook(pd.ctypes.data, buf, len(buf))
+    return buf.raw[:n].decode()
+
+
+def dump_vcd(pd, ch_id="'", header=False):
+    pd = np.ascontiguousarray(pd)
+    buf = C.create_string_buffer(1 << 17)
+    n = lib().refh_dump_vcd(pd.ctypes.data, ord(ch_id), int(header), buf, len(buf))
+    return buf.raw[:n].decode()
+
+
+def dump_raw(pd, length, buf_offset, bits):
+    pd = np.ascontiguousarray(pd)
+    out = np.zeros(length, np.uint8)
+    lib().refh_dump_raw(out.ctypes.data, length, buf_offset, pd.ctypes.data, bits)
+    return out
+
+
+def _slice_pulse_data(self, pd):
+    """run_ook_demods / run_fsk_demods of all registered devices on a pulse_data_t record
+    -> [(dev, hash, bitbuffer or None)] in dispatch order."""
+    pd = np.ascontiguousarray(pd).copy()
+    L, h = self.L, self.h
+    n = L.refh_slice_pulse_data(h, pd.ctypes.data)
+    if not n:
+        return []
+    ev = L.refh_events(h)
+    nbb = L.refh_num_bitbuffers(h)
+    bbs = np.frombuffer((C.c_uint8 * (nbb * 6604)).from_address(L.refh_bitbuffers(h)), dtype=BITBUFFER_DTYPE).copy() if nbb else None
+    return [(ev[i].dev, ev[i].hash, bbs[ev[i].bb_idx] if bbs is not None and ev[i].bb_idx != 0xffffffff else None) for i in range(n)]
+
+
+Ref.slice_pulse_data = _slice_pulse_data

@@ -14,6 +14,7 @@
 #include "../../include/r433b_abi.h"
 #include "r433b_kernels.cuh"
 #include "r433b_host.hpp"
+#include "r433b_pulses.hpp"
 
 using namespace r433b;
 
@@ -84,6 +85,14 @@ struct r433b_ctx {
     std::vector<uint64_t> am_offsets; // first sample of stream i in d_am (multiples of the tile), n_streams + 1
     HostBuf h_ranges;
     bool d2h_done = false;
+    // pulse-level input (r433b_process_pulses): per-package facts the package record has no field for;
+    // r433b_package.end_pos is the index into this table
+    bool pulse_mode = false;
+    std::vector<PulseSet::Meta> pulse_meta;
+};
+
+struct r433b_pulses {
+    PulseSet set;
 };
 
 namespace {
@@ -278,6 +287,7 @@ int r433b_process(r433b_ctx *ctx, r433b_batch const *b)
     }
     CU(cudaSetDevice(ctx->device));
     ctx->processed = ctx->fetched = false;
+    ctx->pulse_mode = false;
     ctx->batch = *b;
     ctx->batch.sample_format = (uint32_t)SS; // the host replay only needs the sample size (dm_state.sample_size)
     ctx->batch.block_bytes = block_bytes;
@@ -810,6 +820,7 @@ int r433b_event_to_bitbuffer(uint8_t const *ev, uint32_t pair_bytes, uint32_t in
 float r433b_package_file_pos(r433b_ctx const *ctx, r433b_results const *res, uint32_t package)
 {
     if (!ctx || !res || package >= res->n_packages) return 0.0f;
+    if (ctx->pulse_mode) return 0.0f; // demod->sample_file_pos = 0.0 in front of the .ook loop, src/rtl_433.c:1752
     r433b_package const &k = res->packages[package];
     uint64_t SS = ctx->batch.sample_format;
     uint64_t bytes = ctx->lengths[k.stream];
@@ -829,6 +840,20 @@ int r433b_package_to_pulse_data(r433b_ctx const *ctx, r433b_results const *res, 
     if (!ctx || !res || !pd || package >= res->n_packages) return R433B_EINVAL;
     r433b_package const &k = res->packages[package];
     memset(pd, 0, sizeof(*pd));
+    if (ctx->pulse_mode) {
+        // a loaded package: exactly what pulse_data_load() / rfraw_parse() left in the struct
+        if (k.end_pos >= ctx->pulse_meta.size()) return R433B_EINVAL;
+        PulseSet::Meta const &m = ctx->pulse_meta[k.end_pos];
+        pd->sample_rate = m.rate;
+        pd->num_pulses = m.num_pulses;
+        memcpy(pd->pulse, res->pulse_pool + k.pulse_off, k.pulse_count * sizeof(int));
+        memcpy(pd->gap, res->gap_pool + k.pulse_off, k.pulse_count * sizeof(int));
+        pd->fsk_f1_est = m.fsk_f1_est;
+        pd->fsk_f2_est = m.fsk_f2_est;
+        pd->freq1_hz = m.freq1_hz;
+        pd->freq2_hz = m.freq2_hz;
+        return R433B_OK;
+    }
     pd->offset = k.offset;
     pd->sample_rate = ctx->batch.samp_rate;
     pd->start_ago = k.start_ago;
@@ -981,6 +1006,217 @@ int r433b_dispatch_r_devices(r433b_ctx *ctx, r433b_results const *res, uint32_t 
         }
         return ret;
     });
+}
+
+} // extern "C"
+
+// ------------------------------------------------ pulse-level I/O -----------
+// Packages that never were IQ: `.ook` pulse files and RfRaw lines go straight to k_slice.
+
+extern "C" {
+
+r433b_pulses *r433b_pulses_create(void) { return new (std::nothrow) r433b_pulses(); }
+
+void r433b_pulses_destroy(r433b_pulses *ps) { delete ps; }
+
+void r433b_pulses_clear(r433b_pulses *ps)
+{
+    if (!ps) return;
+    ps->set = PulseSet();
+}
+
+int r433b_pulses_load_ook(r433b_pulses *ps, uint32_t stream, char const *text, size_t len, uint32_t samp_rate)
+{
+    if (!ps || (!text && len) || !samp_rate) return R433B_EINVAL;
+    return load_ook_text(ps->set, stream, text, len, samp_rate);
+}
+
+int r433b_pulses_load_rfraw(r433b_pulses *ps, uint32_t stream, char const *line)
+{
+    if (!ps || !line) return R433B_EINVAL;
+    if (!rfraw_is(line)) return 0;
+    // `pulse_data_t pulse_data = {0}; rfraw_parse(&pulse_data, line);` (src/rtl_433.c:1622-1624, :1639-1641)
+    static thread_local struct pulse_data d;
+    memset(&d, 0, sizeof(d));
+    rfraw_append(&d, line);
+    ps->set.add(stream, &d);
+    return 1;
+}
+
+int r433b_pulses_add(r433b_pulses *ps, uint32_t stream, struct pulse_data const *pd)
+{
+    if (!ps || !pd) return R433B_EINVAL;
+    ps->set.add(stream, pd);
+    return 1;
+}
+
+uint32_t r433b_pulses_count(r433b_pulses const *ps) { return ps ? (uint32_t)ps->set.pk.size() : 0; }
+
+int r433b_pulses_get(r433b_pulses const *ps, uint32_t index, struct pulse_data *out)
+{
+    if (!ps || !out || index >= ps->set.pk.size()) return R433B_EINVAL;
+    ps->set.get(index, out);
+    return R433B_OK;
+}
+
+size_t r433b_format_ook(struct pulse_data const *pd, char const *received, char *buf, size_t cap)
+{
+    return pd ? format_ook(pd, received, buf, cap) : 0;
+}
+
+size_t r433b_format_ook_header(char const *created, char *buf, size_t cap) { return format_ook_header(created, buf, cap); }
+
+size_t r433b_format_vcd(struct pulse_data const *pd, int ch_id, char *buf, size_t cap)
+{
+    return pd ? format_vcd(pd, ch_id, buf, cap) : 0;
+}
+
+size_t r433b_format_vcd_header(uint32_t sample_rate, char const *date, char *buf, size_t cap)
+{
+    return format_vcd_header(sample_rate, date, buf, cap);
+}
+
+void r433b_dump_logic_u8(uint8_t *buf, uint64_t len, uint64_t buf_offset, struct pulse_data const *pd, uint8_t bits)
+{
+    if (buf && pd) dump_logic_u8(buf, len, buf_offset, pd, bits);
+}
+
+// run_ook_demods() / run_fsk_demods() on every package of the set (src/rtl_433.c:1755-1790, :1620-1650): the
+// slicers of all registered devices on the GPU, results fetched and replayed like those of r433b_process().
+// Packages may carry different sample rates (an RfRaw line is 1 MHz whatever the file's rate is): one k_slice
+// launch per distinct rate, each with the device widths scaled to that rate.
+int r433b_process_pulses(r433b_ctx *ctx, r433b_pulses const *ps)
+{
+    if (!ctx || !ps) return fail(ctx, R433B_EINVAL, "null argument");
+    CU(cudaSetDevice(ctx->device));
+    PulseSet const &set = ps->set;
+    uint32_t const n = (uint32_t)set.pk.size();
+    uint32_t const n_devs = (uint32_t)ctx->devs.size();
+    if ((uint64_t)n * n_devs > 0xffffffffull)
+        return fail(ctx, R433B_EOVERFLOW, "packages x devices exceeds the 32-bit pair index (r433b_package.first_pair)");
+    ctx->processed = ctx->fetched = false;
+    ctx->d2h_done = false;
+    ctx->pulse_mode = true;
+    ctx->pulse_meta = set.pk;
+    ctx->batch = r433b_batch{};
+    ctx->batch.sample_format = 2;
+    ctx->offsets.clear();
+    ctx->lengths.clear();
+    cudaStream_t const st = 0;
+
+    // device order: by sample rate (stable), so that every rate is one contiguous package range
+    std::vector<uint32_t> order(n);
+    for (uint32_t i = 0; i < n; ++i) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return set.pk[a].rate < set.pk[b].rate; });
+    std::vector<r433b_package> hp(n);
+    std::vector<int32_t> pp, gp;
+    pp.reserve(set.pulse.size());
+    gp.reserve(set.gap.size());
+    struct RateRange { uint32_t rate, begin, end; };
+    std::vector<RateRange> rates;
+    for (uint32_t j = 0; j < n; ++j) {
+        PulseSet::Meta const &m = set.pk[order[j]];
+        r433b_package &k = hp[j];
+        memset(&k, 0, sizeof(k));
+        k.stream = m.stream;
+        k.seq = m.seq;
+        k.type = m.type;
+        k.end_pos = order[j];
+        k.num_pulses = m.num_pulses;
+        k.pulse_off = (uint32_t)pp.size();
+        k.pulse_count = m.count;
+        k.fsk_f1_est = m.fsk_f1_est;
+        k.fsk_f2_est = m.fsk_f2_est;
+        k.first_pair = j * n_devs;
+        pp.insert(pp.end(), set.pulse.begin() + m.first, set.pulse.begin() + m.first + m.count);
+        gp.insert(gp.end(), set.gap.begin() + m.first, set.gap.begin() + m.first + m.count);
+        if (rates.empty() || rates.back().rate != m.rate) rates.push_back({m.rate, j, j});
+        rates.back().end = j + 1;
+    }
+    for (auto const &r : rates)
+        if (!r.rate) return fail(ctx, R433B_EINVAL, "a package has sample_rate 0");
+
+    ctx->n_pkgs = n;
+    ctx->pool_used = (unsigned)pp.size();
+    ctx->n_samples = 0;
+    ctx->event_bytes = ctx->n_events = 0;
+    ctx->timing = r433b_timing{};
+    std::vector<unsigned> ook = slice_list(ctx->devs, 1), fsk = slice_list(ctx->devs, 2);
+    ctx->n_ook = (unsigned)ook.size();
+    ctx->n_fsk = (unsigned)fsk.size();
+    if (n && n_devs) {
+        if (int r = dev_reserve(ctx, ctx->d_pkgs, (size_t)n * sizeof(r433b_package))) return r;
+        if (int r = dev_reserve(ctx, ctx->d_ppool, pp.size() * sizeof(int) + 16)) return r;
+        if (int r = dev_reserve(ctx, ctx->d_gpool, gp.size() * sizeof(int) + 16)) return r;
+        size_t const pair_bytes = (size_t)n * n_devs * sizeof(r433b_pair);
+        if (int r = dev_reserve(ctx, ctx->d_pairs, pair_bytes)) return r;
+        if (int r = dev_reserve(ctx, ctx->d_ranges, rates.size() * sizeof(GroupRange))) return r;
+        if (int r = dev_reserve(ctx, ctx->d_devparams, rates.size() * n_devs * sizeof(SlicerParams))) return r;
+        if (int r = dev_reserve(ctx, ctx->d_lists, (ook.size() + fsk.size() + 1) * sizeof(unsigned))) return r;
+        if (int r = dev_reserve(ctx, ctx->d_cursor, 64)) return r;
+        unsigned const slice_grid = (unsigned)ctx->n_sms * kSliceCtasPerSm;
+        if (int r = dev_reserve(ctx, ctx->d_stage, (size_t)slice_grid * kSliceThreads * ctx->stage_words * sizeof(uint32_t))) return r;
+        if (ctx->arena_cap < (size_t)(1u << 20)) ctx->arena_cap = 1u << 20;
+        std::vector<SlicerParams> sp(rates.size() * n_devs);
+        std::vector<GroupRange> rg(rates.size());
+        for (size_t g = 0; g < rates.size(); ++g) {
+            for (uint32_t i = 0; i < n_devs; ++i) sp[g * n_devs + i] = scale_device(ctx->devs[i], rates[g].rate);
+            rg[g] = GroupRange{};
+            rg[g].pkg_begin = rates[g].begin;
+            rg[g].pkg_end = rates[g].end;
+        }
+        CU(cudaMemcpyAsync(ctx->d_pkgs.p, hp.data(), (size_t)n * sizeof(r433b_package), cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(ctx->d_ppool.p, pp.data(), pp.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(ctx->d_gpool.p, gp.data(), gp.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(ctx->d_devparams.p, sp.data(), sp.size() * sizeof(SlicerParams), cudaMemcpyHostToDevice, st));
+        if (!ook.empty()) CU(cudaMemcpyAsync(ctx->d_lists.p, ook.data(), ook.size() * sizeof(unsigned), cudaMemcpyHostToDevice, st));
+        if (!fsk.empty())
+            CU(cudaMemcpyAsync((unsigned *)ctx->d_lists.p + ook.size(), fsk.data(), fsk.size() * sizeof(unsigned), cudaMemcpyHostToDevice, st));
+        unsigned long long cursor[4] = {0, 0, 0, 0};
+        CU(cudaEventRecord(ctx->ev[2], st));
+        for (int attempt = 0; attempt < 3; ++attempt) {
+            if (int r = dev_reserve(ctx, ctx->d_arena, ctx->arena_cap)) return r;
+            CU(cudaMemsetAsync(ctx->d_pairs.p, 0, pair_bytes, st));
+            CU(cudaMemsetAsync(ctx->d_cursor.p, 0, 64, st));
+            CU(cudaMemcpyAsync(ctx->d_ranges.p, rg.data(), rg.size() * sizeof(GroupRange), cudaMemcpyHostToDevice, st));
+            for (size_t g = 0; g < rates.size(); ++g) {
+                SliceParams q{};
+                q.pkgs = (r433b_package *)ctx->d_pkgs.p;
+                q.n_pkgs = n;
+                q.range = (GroupRange *)ctx->d_ranges.p + g;
+                q.pulse_pool = (int const *)ctx->d_ppool.p;
+                q.gap_pool = (int const *)ctx->d_gpool.p;
+                q.dev = (SlicerParams const *)ctx->d_devparams.p + g * n_devs;
+                q.n_devs = n_devs;
+                q.ook_list = (unsigned const *)ctx->d_lists.p;
+                q.fsk_list = (unsigned const *)ctx->d_lists.p + ook.size();
+                q.n_ook = ctx->n_ook;
+                q.n_fsk = ctx->n_fsk;
+                q.pairs = (r433b_pair *)ctx->d_pairs.p;
+                q.arena = (uint8_t *)ctx->d_arena.p;
+                q.arena_cap = ctx->arena_cap;
+                q.cursor = (unsigned long long *)ctx->d_cursor.p;
+                q.stage = (uint32_t *)ctx->d_stage.p;
+                q.stage_words = ctx->stage_words;
+                R4_LAUNCH(k_slice, slice_grid, kSliceThreads, 0, st, q);
+                CU(cudaGetLastError());
+                ctx->timing.slice_launches++;
+            }
+            CU(cudaMemcpyAsync(cursor, ctx->d_cursor.p, sizeof(cursor), cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+            if (!cursor[2]) break;
+            ctx->arena_cap = (size_t)cursor[0] + (1u << 20);
+            if (attempt == 2) return fail(ctx, R433B_EOVERFLOW, "event arena overflow");
+        }
+        CU(cudaEventRecord(ctx->ev[3], st));
+        CU(cudaEventSynchronize(ctx->ev[3]));
+        cudaEventElapsedTime(&ctx->timing.slice_ms, ctx->ev[2], ctx->ev[3]);
+        ctx->timing.total_ms = ctx->timing.slice_ms;
+        ctx->event_bytes = cursor[0];
+        ctx->n_events = cursor[1];
+    }
+    ctx->processed = true;
+    return R433B_OK;
 }
 
 } // extern "C"

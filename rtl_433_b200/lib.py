@@ -25,7 +25,11 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
 EXPORTS = ["r433b_create", "r433b_destroy", "r433b_last_error", "r433b_set_levels", "r433b_set_fm_low_pass",
            "r433b_set_devices", "r433b_set_r_devices", "r433b_set_pipeline", "r433b_process", "r433b_fetch", "r433b_get_timing",
            "r433b_get_counts", "r433b_copy_stage", "r433b_event_to_bitbuffer", "r433b_package_to_pulse_data",
-           "r433b_package_file_pos", "r433b_dispatch", "r433b_dispatch_r_devices", "r433b_stream_digest"]
+           "r433b_package_file_pos", "r433b_dispatch", "r433b_dispatch_r_devices", "r433b_stream_digest",
+           "r433b_pulses_create", "r433b_pulses_destroy", "r433b_pulses_clear", "r433b_pulses_load_ook",
+           "r433b_pulses_load_rfraw", "r433b_pulses_add", "r433b_pulses_count", "r433b_pulses_get", "r433b_process_pulses",
+           "r433b_format_ook", "r433b_format_ook_header", "r433b_format_vcd", "r433b_format_vcd_header",
+           "r433b_dump_logic_u8"]
 
 
 def build(force=False, verbose=False):
@@ -133,6 +137,23 @@ def load():
     L.r433b_package_file_pos.argtypes = [C.c_void_p, C.POINTER(Results), C.c_uint32]
     L.r433b_dispatch.argtypes = [C.c_void_p, C.POINTER(Results), C.c_uint32, EVENT_FN, C.c_void_p]
     L.r433b_dispatch_r_devices.argtypes = [C.c_void_p, C.POINTER(Results), C.c_uint32, C.c_void_p, C.c_uint32]
+    L.r433b_pulses_create.restype = C.c_void_p
+    L.r433b_pulses_destroy.argtypes = [C.c_void_p]
+    L.r433b_pulses_clear.argtypes = [C.c_void_p]
+    L.r433b_pulses_load_ook.argtypes = [C.c_void_p, C.c_uint32, C.c_char_p, C.c_size_t, C.c_uint32]
+    L.r433b_pulses_load_rfraw.argtypes = [C.c_void_p, C.c_uint32, C.c_char_p]
+    L.r433b_pulses_add.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
+    L.r433b_pulses_count.restype = C.c_uint32
+    L.r433b_pulses_count.argtypes = [C.c_void_p]
+    L.r433b_pulses_get.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
+    L.r433b_process_pulses.argtypes = [C.c_void_p, C.c_void_p]
+    for name in ("r433b_format_ook", "r433b_format_ook_header", "r433b_format_vcd", "r433b_format_vcd_header"):
+        getattr(L, name).restype = C.c_size_t
+    L.r433b_format_ook.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_size_t]
+    L.r433b_format_ook_header.argtypes = [C.c_char_p, C.c_char_p, C.c_size_t]
+    L.r433b_format_vcd.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_size_t]
+    L.r433b_format_vcd_header.argtypes = [C.c_uint32, C.c_char_p, C.c_char_p, C.c_size_t]
+    L.r433b_dump_logic_u8.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_uint8]
     _lib = L
     return L
 
@@ -146,6 +167,103 @@ def default_device_table(include_disabled=False):
 
 class R433Error(RuntimeError):
     pass
+
+
+PULSE_DATA_DTYPE = np.dtype([("offset", "<u8"), ("sample_rate", "<u4"), ("depth_bits", "<u4"), ("start_ago", "<u4"),
+                             ("end_ago", "<u4"), ("num_pulses", "<u4"), ("pulse", "<i4", (1200,)), ("gap", "<i4", (1200,)),
+                             ("ook_low_estimate", "<i4"), ("ook_high_estimate", "<i4"), ("fsk_f1_est", "<i4"),
+                             ("fsk_f2_est", "<i4"), ("freq1_hz", "<f4"), ("freq2_hz", "<f4"), ("centerfreq_hz", "<f4"),
+                             ("range_db", "<f4"), ("rssi_db", "<f4"), ("snr_db", "<f4"), ("noise_db", "<f4")], align=True)
+assert PULSE_DATA_DTYPE.itemsize == 9672
+
+
+def _as_pd_ptr(pd):
+    """ctypes PulseData or numpy PULSE_DATA_DTYPE record -> (address, keep-alive object)."""
+    if isinstance(pd, PulseData):
+        return C.addressof(pd), pd
+    a = np.ascontiguousarray(pd, dtype=PULSE_DATA_DTYPE).reshape(-1)[:1].copy()
+    return a.ctypes.data, a
+
+
+class Pulses:
+    """A set of loaded packages (include/r433b.h: r433b_pulses): `.ook` text, RfRaw lines, pulse_data_t records.
+    Host only; Context.process_pulses() runs the slicers on it."""
+
+    def __init__(self):
+        self.L = load()
+        self.h = C.c_void_p(self.L.r433b_pulses_create())
+        if not self.h:
+            raise R433Error("r433b_pulses_create failed")
+
+    def close(self):
+        if self.h:
+            self.L.r433b_pulses_destroy(self.h)
+            self.h = None
+
+    def clear(self):
+        self.L.r433b_pulses_clear(self.h)
+
+    def load_ook(self, text, samp_rate, stream=0):
+        if isinstance(text, str):
+            text = text.encode()
+        n = self.L.r433b_pulses_load_ook(self.h, stream, text, len(text), samp_rate)
+        if n < 0:
+            raise R433Error(f"r433b_pulses_load_ook: {n}")
+        return n
+
+    def load_rfraw(self, line, stream=0):
+        n = self.L.r433b_pulses_load_rfraw(self.h, stream, line.encode() if isinstance(line, str) else line)
+        if n < 0:
+            raise R433Error(f"r433b_pulses_load_rfraw: {n}")
+        return n
+
+    def add(self, pd, stream=0):
+        ptr, _keep = _as_pd_ptr(pd)
+        return self.L.r433b_pulses_add(self.h, stream, ptr)
+
+    def __len__(self):
+        return self.L.r433b_pulses_count(self.h)
+
+    def get(self, i):
+        out = np.zeros(1, PULSE_DATA_DTYPE)
+        rc = self.L.r433b_pulses_get(self.h, i, out.ctypes.data)
+        if rc:
+            raise R433Error(f"r433b_pulses_get: {rc}")
+        return out[0]
+
+
+def format_ook(pd, received=None):
+    """pulse_data_dump() text of a pulse_data_t (src/pulse_data.c:193-226)."""
+    ptr, _keep = _as_pd_ptr(pd)
+    buf = C.create_string_buffer(1 << 16)
+    n = load().r433b_format_ook(ptr, received.encode() if received is not None else None, buf, len(buf))
+    return buf.raw[:n].decode()
+
+
+def format_vcd(pd, ch_id="'"):
+    ptr, _keep = _as_pd_ptr(pd)
+    buf = C.create_string_buffer(1 << 17)
+    n = load().r433b_format_vcd(ptr, ord(ch_id), buf, len(buf))
+    return buf.raw[:n].decode()
+
+
+def format_vcd_header(sample_rate, date=""):
+    buf = C.create_string_buffer(1024)
+    n = load().r433b_format_vcd_header(sample_rate, date.encode(), buf, len(buf))
+    return buf.raw[:n].decode()
+
+
+def format_ook_header(created=None):
+    buf = C.create_string_buffer(256)
+    n = load().r433b_format_ook_header(created.encode() if created is not None else None, buf, len(buf))
+    return buf.raw[:n].decode()
+
+
+def dump_logic_u8(pd, length, buf_offset, bits):
+    ptr, _keep = _as_pd_ptr(pd)
+    out = np.zeros(length, np.uint8)
+    load().r433b_dump_logic_u8(out.ctypes.data, length, buf_offset, ptr, bits)
+    return out
 
 
 class Context:
@@ -203,6 +321,11 @@ class Context:
                   None if lens is None else lens.ctypes.data_as(C.POINTER(C.c_uint64)))
         self._keep = (data, offs, lens)
         self._check(self.L.r433b_process(self.h, C.byref(b)))
+
+    def process_pulses(self, pulses):
+        """All slicers on every package of a Pulses set (k_slice only); then fetch()/dispatch as usual."""
+        self._keep = pulses
+        self._check(self.L.r433b_process_pulses(self.h, pulses.h))
 
     def counts(self):
         out = (C.c_uint64 * 4)()

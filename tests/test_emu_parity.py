@@ -33,6 +33,13 @@ from test_gpu_parity import (ctx, devices,  # noqa: E402,F401  (fixtures)
                              test_ook_cu8_default_devices, test_pipelined_time_slices_identical,
                              test_priority_classes_stop_after_a_decode, test_ragged_lengths_and_small_blocks,
                              test_rates_and_formats_round_1_never_compared, test_silence_and_reference_vectors)
+import test_pulse_io  # noqa: E402
+
+
+@test_pulse_io.needs_ref
+def test_emu_loaded_packages_through_k_slice():
+    """r433b_process_pulses under the emulator: the body of the -m gpu test."""
+    test_pulse_io.loaded_packages_through_k_slice()
 
 
 def test_emu_reverse_schedule(devices):
