@@ -94,7 +94,9 @@ typedef struct r433b_package {
 typedef struct r433b_pair {
     uint64_t offset;
     uint32_t bytes;
-    uint32_t events;
+    uint32_t events;       /* events stored in the arena */
+    uint32_t gated_single; /* events dropped by the device's gate (r433b_set_gates): bitbuffers of one row ... */
+    uint32_t gated_multi;  /* ... and of several rows */
 } r433b_pair;
 
 /* Host view of a processed batch; pointers stay valid until the next r433b_process(). */
@@ -107,8 +109,9 @@ typedef struct r433b_results {
     r433b_pair const *pairs;       /* n_packages * n_devices, row = package */
     uint8_t const *events;         /* event arena */
     uint64_t event_bytes;
-    uint64_t n_events;
+    uint64_t n_events;             /* events stored */
     uint64_t n_samples;            /* IQ samples consumed */
+    uint64_t n_gated;              /* events counted but not stored (r433b_set_gates) */
 } r433b_results;
 
 /* Wall/device timing of the last r433b_process(), milliseconds. */
@@ -140,14 +143,33 @@ int r433b_set_devices(r433b_ctx *ctx, r433b_device const *devs, uint32_t n);
 struct r_device;
 int r433b_set_r_devices(r433b_ctx *ctx, struct r_device *const *devs, uint32_t n);
 
+/* Decoder length gates (the dispatch fan-out of src/r_api.c:438-550 / src/pulse_slicer.c:26-66).
+   Most events a slicer emits on noise are a few bits long, and every decoder turns those down with its first length
+   check (DECODE_ABORT_LENGTH / _EARLY, include/r_device.h:45-53).  A gate tells the slicer kernel what that check is:
+   an event with at least one row whose rows ALL hold fewer than min_bits bits is not stored; it is only counted, per
+   (package, device), separately for one-row and several-row bitbuffers (many decoders test num_rows first).
+   r433b_dispatch_r_devices() then books the counts exactly as account_event() would have: decode_events += n,
+   decode_fails[-code] += n -- the decoders' statistics stay identical, the events never cross PCIe.  r433b_dispatch()
+   does not call back for gated events (r433b_pair.gated_* has the counts).  One entry per registered device, in
+   registration order; min_bits 0 = no gate.  r433b_set_devices() clears the gates.  The table for the reference's
+   decoders (rtl_433_b200/data/gates_25.12.json) is derived from the decoders themselves by tools/probe_gates.py. */
+typedef struct r433b_gate {
+    uint16_t min_bits;
+    int8_t code_single; /* decode_fn's return (0 .. -4) for a gated one-row event */
+    int8_t code_multi;  /* ... for a gated event of several rows */
+} r433b_gate;
+int r433b_set_gates(r433b_ctx *ctx, r433b_gate const *gates, uint32_t n);
+
 /* rtl_433 -r on every stream of the batch: block loop, flush, reset (src/rtl_433.c:1797-1854),
    then all slicers on every package.  Synchronous; results stay on the device until fetched. */
 int r433b_process(r433b_ctx *ctx, r433b_batch const *batch);
 /* Copy the compact results to host memory owned by the context. */
 int r433b_fetch(r433b_ctx *ctx, r433b_results *out);
 int r433b_get_timing(r433b_ctx const *ctx, r433b_timing *out);
-/* Counters available right after r433b_process() without a fetch: packages, events, event bytes. */
+/* Counters available right after r433b_process() without a fetch: packages, events stored, event bytes, samples. */
 int r433b_get_counts(r433b_ctx const *ctx, uint64_t out[4]);
+/* Events the gates dropped in the last batch (counted on the device). */
+uint64_t r433b_get_gated(r433b_ctx const *ctx);
 
 /* Stage arrays of one stream (batch.want_stages): what dm_state.am_buf / buf.fm held. */
 int r433b_copy_stage(r433b_ctx *ctx, uint32_t stream, int16_t *am, int16_t *fm, uint64_t max_samples);
@@ -181,6 +203,45 @@ int r433b_dispatch(r433b_ctx *ctx, r433b_results const *res, uint32_t stream, r4
    exactly as account_event() does (src/pulse_slicer.c:26-66). */
 int r433b_dispatch_r_devices(r433b_ctx *ctx, r433b_results const *res, uint32_t stream,
         struct r_device *const *devs, uint32_t n);
+/* Threaded replay: stream s is replayed by worker s % n_sets, each worker calling the decoders of its
+   own set of r_device instances (dev_sets[w][0 .. n_devs): registered separately, so statistics and decoder contexts
+   are per worker; one instance is never entered by two threads).  Order within a stream is the reference's.  The
+   caller adds up the per-set statistics.  Decoders that keep file-scope state between calls (secplus_v1/v2,
+   ikea_sparsnas, arad_ms_meter in 25.12) see the streams of one worker only, in that worker's order. */
+int r433b_dispatch_r_devices_parallel(r433b_ctx *ctx, r433b_results const *res, struct r_device *const *const *dev_sets,
+        uint32_t n_devs, uint32_t n_sets);
+
+/* ---- pulse analyzer: `rtl_433 -A`, src/pulse_analyzer.c:279-560, for every package of a batch ----
+   The five width histograms of each package are built on the GPU (one thread per package and histogram), the guess
+   of the modulation, the RfRaw rendering and the text are finished on the host from those bins, and the trial
+   demodulation runs each package through the slicer of ITS guessed flex device on the GPU again. */
+typedef struct r433b_hist_bin { /* hist_bin_t, src/pulse_analyzer.c:23-29 */
+    uint32_t count;
+    int32_t sum, mean, min, max;
+} r433b_hist_bin;
+typedef struct r433b_histogram { /* histogram_t, :32-35 */
+    uint32_t bins_count;
+    r433b_hist_bin bins[16];
+} r433b_histogram;
+typedef struct r433b_analysis {
+    r433b_histogram hist[5]; /* as printed: pulses, gaps, pulse+gap periods, gap+pulse periods, all timings (fused) */
+    int32_t total_period;    /* pulse_total_period, :289-296 */
+} r433b_analysis;
+typedef struct r433b_guess { /* the "Analyzer Device" the reference fills in, :355-459 */
+    uint32_t modulation;     /* include/r_device.h:24-40, 0 = no clue */
+    float short_width, long_width, reset_limit, gap_limit, sync_width, tolerance;
+    int32_t last_gap;        /* >= 0: the package's last gap is overwritten with this before slicing (:531,:538,:545,:551) */
+    int32_t sliced;          /* the reference calls a slicer for this guess */
+} r433b_guess;
+/* Analyze every package of the fetched batch (after r433b_fetch()). */
+int r433b_analyze(r433b_ctx *ctx, r433b_results const *res);
+int r433b_analysis_get(r433b_ctx const *ctx, r433b_results const *res, uint32_t package, r433b_analysis *out, r433b_guess *guess);
+/* The text pulse_analyzer() prints to stderr for the package, up to the trial demodulation's own log output
+   (snprintf convention). */
+size_t r433b_analysis_text(r433b_ctx const *ctx, r433b_results const *res, uint32_t package, char *buf, size_t cap);
+/* The events of the trial demodulation (compact wire format, see r433b_event_to_bitbuffer). */
+int r433b_analysis_events(r433b_ctx const *ctx, r433b_results const *res, uint32_t package, uint8_t const **events,
+        uint32_t *bytes, uint32_t *n_events);
 
 /* ---- pulse-level I/O: packages that never were IQ --------------------------------------
    `rtl_433 -r file.ook` (src/rtl_433.c:1755-1790) and RfRaw test data (-y, src/rtl_433.c:1620-1650) skip the

@@ -121,8 +121,9 @@ static void sink_log(r_device *d, int level, data_t *data)
 
 static void sink_output(r_device *d, data_t *data)
 {
-    (void)d;
-    refh_t *h = g_active;
+    /* register_protocol() stores the r_cfg_t in output_ctx and the cfg is the first member of refh_t: with several
+       harness instances dispatching at once (threaded dispatch tests) every decoder reports to its own instance */
+    refh_t *h = d->output_ctx ? (refh_t *)d->output_ctx : g_active;
     if (h) {
         h->decoded_msgs++;
         char buf[4096];
@@ -729,4 +730,102 @@ REFH_EXPORT int refh_slice_pulse_data(refh_t *h, pulse_data_t *pd)
     free(all.elems);
     g_active = NULL;
     return (int)h->n_evts;
+}
+
+/* -------- decoder length gates: what does decode_fn do with events that are too short? --------
+   For device idx find the largest T <= max_bits such that EVERY probed bitbuffer with at least one row whose rows all
+   hold fewer than T bits makes the decoder return a constant code <= 0 without producing output -- code[0] for buffers
+   of one row, code[1] for buffers of several (many decoders test num_rows first): all 2^L contents of a single row
+   of L bits (exhaustive, L < T), and n_random more bitbuffers per L (random row count, lengths <= L with one row of
+   exactly L, random bytes -- also beyond the row lengths --, random sync counts).  Returns T. */
+static uint64_t probe_rng(uint64_t *s)
+{
+    *s ^= *s << 13; *s ^= *s >> 7; *s ^= *s << 17;
+    return *s;
+}
+
+static int probe_call(refh_t *h, int idx, bitbuffer_t const *bb, int *out_delta)
+{
+    static bitbuffer_t work;
+    work = *bb;
+    uint64_t before = h->decoded_msgs;
+    int ret = h->orig_fn[idx] ? h->orig_fn[idx](h->devs[idx], &work) : 0;
+    *out_delta = (int)(h->decoded_msgs - before);
+    return ret;
+}
+
+REFH_EXPORT int refh_probe_gate(refh_t *h, int idx, int max_bits, int n_random, uint64_t seed, int code[2])
+{
+    code[0] = code[1] = 0;
+    if (idx < 0 || idx >= h->n_devs || !h->orig_fn[idx]) return 0;
+    refh_t *saved = g_active;
+    g_active = h;
+    static bitbuffer_t bb;
+    int delta = 0;
+    /* c1: one empty row; cN: two empty rows.  (A buffer without any row -- an nrzs event can be one -- is never gated.) */
+    memset(&bb, 0, sizeof(bb));
+    bb.num_rows = bb.free_row = 1;
+    int const c1 = probe_call(h, idx, &bb, &delta);
+    int bad = delta;
+    bb.num_rows = bb.free_row = 2;
+    int const cN = probe_call(h, idx, &bb, &delta);
+    bad |= delta;
+    code[0] = c1;
+    code[1] = cN;
+    int T = 0;
+    if (bad || c1 > 0 || c1 < -4 || cN > 0 || cN < -4) { g_active = saved; return 0; }
+    uint64_t rng = seed * 0x9E3779B97F4A7C15ull + 0x1234567ull + (uint64_t)idx;
+    for (int L = 0; L < max_bits; ++L) {
+        int ok = 1;
+        /* one row of exactly L bits, every content */
+        for (uint32_t v = 0; ok && v < (1u << L); ++v) {
+            memset(&bb, 0, 204 + 8);
+            bb.num_rows = 1;
+            bb.free_row = 1;
+            bb.bits_per_row[0] = (uint16_t)L;
+            uint32_t left = L ? v << (32 - L) : 0;
+            bb.bb[0][0] = left >> 24; bb.bb[0][1] = left >> 16; bb.bb[0][2] = left >> 8; bb.bb[0][3] = left;
+            if (probe_call(h, idx, &bb, &delta) != c1 || delta) ok = 0;
+        }
+        /* one row with dirt beyond its length and sync counts; two or more rows, none longer than L */
+        for (int k = 0; ok && k < n_random; ++k) {
+            memset(&bb, 0, sizeof(bb));
+            uint64_t r = probe_rng(&rng);
+            int rows = k % 8 == 0 ? 1 : 2 + (int)(r % ((r >> 8) % 4 == 0 ? 49 : 5));
+            int longest = (int)((r >> 16) % rows);
+            int mode = (int)((r >> 24) % 5); /* random / zeros / ones / 0xaa / 0x55 */
+            bb.num_rows = (uint16_t)rows;
+            bb.free_row = (uint16_t)rows;
+            for (int row = 0; row < rows; ++row) {
+                uint64_t q = probe_rng(&rng);
+                int bits = row == longest ? L : (int)(q % (L + 1));
+                bb.bits_per_row[row] = (uint16_t)bits;
+                bb.syncs_before_row[row] = (q >> 20) % 7 == 0 ? (uint16_t)((q >> 24) % 4) : 0;
+                for (int b = 0; b < 4; ++b) {
+                    uint8_t byte = mode == 0 ? (uint8_t)(q >> (32 + 8 * b)) : mode == 1 ? 0 : mode == 2 ? 0xff : mode == 3 ? 0xaa : 0x55;
+                    /* half of the random buffers are clean beyond the row length, as the bit writer leaves them */
+                    if ((r >> 40) & 1) {
+                        int keep = bits - 8 * b;
+                        byte = keep <= 0 ? 0 : keep >= 8 ? byte : (uint8_t)(byte & (0xff00 >> keep));
+                    }
+                    bb.bb[row][b] = byte;
+                }
+            }
+            if (probe_call(h, idx, &bb, &delta) != (rows == 1 ? c1 : cN) || delta) ok = 0;
+        }
+        if (!ok) break;
+        T = L + 1;
+    }
+    g_active = saved;
+    return T;
+}
+
+/* decode_fn of device idx on one bitbuffer (validation of a gate table with independent inputs) */
+REFH_EXPORT int refh_call_decoder(refh_t *h, int idx, bitbuffer_t const *bb, int *outputs)
+{
+    refh_t *saved = g_active;
+    g_active = h;
+    int ret = probe_call(h, idx, bb, outputs);
+    g_active = saved;
+    return ret;
 }

@@ -7,7 +7,9 @@
 #include <cstdlib>
 #include <chrono>
 #include <cstring>
+#include <atomic>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/r433b.h"
@@ -53,6 +55,7 @@ struct r433b_ctx {
     int use_mag = 0;
     float level_limit = 0.0f, min_level = -12.1442f, min_snr = 9.0f, fm_low_pass = 0.0f;
     std::vector<r433b_device> devs;
+    std::vector<r433b_gate> gates; // empty, or one per device (r433b_set_gates)
     // last batch (kept for the host replay)
     r433b_batch batch{};
     std::vector<uint64_t> offsets, lengths; // lengths[i] = bytes of stream i in use
@@ -71,7 +74,7 @@ struct r433b_ctx {
     unsigned n_ook = 0, n_fsk = 0;
     // counts of the last batch
     unsigned n_pkgs = 0, pool_used = 0;
-    unsigned long long event_bytes = 0, n_events = 0, n_samples = 0;
+    unsigned long long event_bytes = 0, n_events = 0, n_samples = 0, n_gated = 0;
     // pinned host result buffers
     HostBuf h_pkgs, h_ppool, h_gpool, h_pairs, h_events;
     r433b_timing timing{};
@@ -244,13 +247,28 @@ int r433b_set_devices(r433b_ctx *ctx, r433b_device const *devs, uint32_t n)
 {
     if (!ctx || (n && !devs)) return R433B_EINVAL;
     ctx->devs.assign(devs, devs + n);
+    ctx->gates.clear();
     return R433B_OK;
 }
+
+int r433b_set_gates(r433b_ctx *ctx, r433b_gate const *gates, uint32_t n)
+{
+    if (!ctx || (n && !gates)) return R433B_EINVAL;
+    if (n && n != ctx->devs.size()) return fail(ctx, R433B_EINVAL, "r433b_set_gates: one gate per registered device");
+    for (uint32_t i = 0; i < n; ++i)
+        if (gates[i].code_single > 0 || gates[i].code_single < -4 || gates[i].code_multi > 0 || gates[i].code_multi < -4)
+            return fail(ctx, R433B_EINVAL, "r433b_set_gates: codes are decode_fn returns 0 .. -4");
+    ctx->gates.assign(gates, gates + n);
+    return R433B_OK;
+}
+
+uint64_t r433b_get_gated(r433b_ctx const *ctx) { return ctx && ctx->processed ? ctx->n_gated : 0; }
 
 int r433b_set_r_devices(r433b_ctx *ctx, struct r_device *const *devs, uint32_t n)
 {
     if (!ctx || (n && !devs)) return R433B_EINVAL;
     ctx->devs.resize(n);
+    ctx->gates.clear();
     for (uint32_t i = 0; i < n; ++i) {
         struct r_device const *d = devs[i];
         r433b_device &o = ctx->devs[i];
@@ -425,7 +443,10 @@ int r433b_process(r433b_ctx *ctx, r433b_batch const *b)
 
     // slicer parameters: per device, scaled to this batch's sample rate on the host
     std::vector<SlicerParams> sp(n_devs);
-    for (uint32_t i = 0; i < n_devs; ++i) sp[i] = scale_device(ctx->devs[i], b->samp_rate);
+    for (uint32_t i = 0; i < n_devs; ++i) {
+        sp[i] = scale_device(ctx->devs[i], b->samp_rate);
+        if (!ctx->gates.empty()) sp[i].gate = ctx->gates[i].min_bits;
+    }
     // which devices look at OOK / FSK packages, in the order k_slice's warps take them
     std::vector<unsigned> ook = slice_list(ctx->devs, 1), fsk = slice_list(ctx->devs, 2);
     ctx->n_ook = (unsigned)ook.size();
@@ -590,6 +611,7 @@ int r433b_process(r433b_ctx *ctx, r433b_batch const *b)
             ctx->pool_used = last.pool_end;
             ctx->event_bytes = last.arena_end;
             ctx->n_events = last.events_end;
+            ctx->n_gated = last.gated_end;
             ctx->n_samples = used_bytes / SS;
             ctx->d2h_done = d2h_ok;
             float det = 0, slc = 0, frt = 0;
@@ -703,6 +725,7 @@ int r433b_process(r433b_ctx *ctx, r433b_batch const *b)
     }
     ctx->event_bytes = cursor[0];
     ctx->n_events = cursor[1];
+    ctx->n_gated = cursor[3];
     ctx->n_samples = used_bytes / SS;
     CU(cudaEventRecord(ctx->ev[3], st));
     CU(cudaEventSynchronize(ctx->ev[3]));
@@ -789,6 +812,7 @@ int r433b_fetch(r433b_ctx *ctx, r433b_results *out)
     out->event_bytes = ctx->event_bytes;
     out->n_events = ctx->n_events;
     out->n_samples = ctx->n_samples;
+    out->n_gated = ctx->n_gated;
     return R433B_OK;
 }
 
@@ -896,8 +920,8 @@ int r433b_package_to_pulse_data(r433b_ctx const *ctx, r433b_results const *res, 
 
 namespace {
 
-template <class PerEvent>
-int replay_stream(r433b_ctx *ctx, r433b_results const *res, uint32_t stream, PerEvent &&per_event)
+template <class PerEvent, class PerPair>
+int replay_stream(r433b_ctx *ctx, r433b_results const *res, uint32_t stream, PerEvent &&per_event, PerPair &&per_pair)
 {
     if (!ctx || !res) return R433B_EINVAL;
     if (!ctx->fetched) return fail(ctx, R433B_ESTATE, "dispatch before fetch");
@@ -921,6 +945,7 @@ int replay_stream(r433b_ctx *ctx, r433b_results const *res, uint32_t stream, Per
                 if (dp != prio) continue;
                 if (!device_takes((int)ctx->devs[dv].modulation, k->type)) continue;
                 r433b_pair const &pr = res->pairs[(size_t)k->first_pair + dv];
+                per_pair(dv, pr); // the slicer of this device ran: its gated events were handed over too (and turned down)
                 uint32_t at = 0;
                 for (uint32_t e = 0; e < pr.events; ++e) {
                     uint32_t used = 0;
@@ -972,6 +997,8 @@ int r433b_stream_digest(r433b_ctx *ctx, r433b_results const *res, uint32_t strea
             r433b_pair const &pr = res->pairs[(size_t)k->first_pair + dv];
             mix(pr.bytes);
             mix(pr.events);
+            mix(pr.gated_single);
+            mix(pr.gated_multi);
             if (pr.bytes) mix_words(res->events + pr.offset, pr.bytes / 4);
         }
     }
@@ -984,7 +1011,7 @@ int r433b_dispatch(r433b_ctx *ctx, r433b_results const *res, uint32_t stream, r4
     if (!fn) return R433B_EINVAL;
     return replay_stream(ctx, res, stream, [&](uint32_t pk, uint32_t dv, struct pulse_data *pd, struct bitbuffer *bits) {
         return fn(user, pk, dv, pd, bits);
-    });
+    }, [](uint32_t, r433b_pair const &) {});
 }
 
 int r433b_dispatch_r_devices(r433b_ctx *ctx, r433b_results const *res, uint32_t stream, struct r_device *const *devs,
@@ -1005,7 +1032,47 @@ int r433b_dispatch_r_devices(r433b_ctx *ctx, r433b_results const *res, uint32_t 
             ret = 0;
         }
         return ret;
+    }, [&](uint32_t dv, r433b_pair const &pr) {
+        // gated events: account_event() with the return code the decoder's own length check gives
+        if (!(pr.gated_single | pr.gated_multi) || ctx->gates.size() != n) return;
+        struct r_device *d = devs[dv];
+        r433b_gate const &g = ctx->gates[dv];
+        d->decode_events += pr.gated_single + pr.gated_multi;
+        d->decode_fails[-g.code_single] += pr.gated_single;
+        d->decode_fails[-g.code_multi] += pr.gated_multi;
     });
+}
+
+} // extern "C"
+
+// ------------------------------------------------ threaded replay ------------
+extern "C" {
+
+// The replay of different streams is independent: stream s goes to worker s % n_sets, every worker with its OWN decoder
+// instances (dev_sets[w][0..n_devs): separately registered r_device structs -- the counters and decoder contexts are
+// per instance; the reference's decoders are not re-entrant on one instance).  Within a stream the order is the
+// reference's.  The caller sums the per-set statistics.  Returns the first error of any worker.
+int r433b_dispatch_r_devices_parallel(r433b_ctx *ctx, r433b_results const *res, struct r_device *const *const *dev_sets,
+        uint32_t n_devs, uint32_t n_sets)
+{
+    if (!ctx || !res || !dev_sets || !n_sets || n_devs != res->n_devices) return R433B_EINVAL;
+    if (!ctx->fetched) return fail(ctx, R433B_ESTATE, "dispatch before fetch");
+    uint32_t const n_streams = res->n_packages ? res->packages[res->n_packages - 1].stream + 1 : 0;
+    std::atomic<int> first_error{0};
+    auto work = [&](uint32_t w) {
+        for (uint32_t s = w; s < n_streams && !first_error.load(std::memory_order_relaxed); s += n_sets) {
+            int rc = r433b_dispatch_r_devices(ctx, res, s, dev_sets[w], n_devs);
+            if (rc) {
+                int expected = 0;
+                first_error.compare_exchange_strong(expected, rc);
+            }
+        }
+    };
+    std::vector<std::thread> pool;
+    for (uint32_t w = 1; w < n_sets; ++w) pool.emplace_back(work, w);
+    work(0);
+    for (auto &t : pool) t.join();
+    return first_error.load();
 }
 
 } // extern "C"
@@ -1139,7 +1206,7 @@ int r433b_process_pulses(r433b_ctx *ctx, r433b_pulses const *ps)
     ctx->n_pkgs = n;
     ctx->pool_used = (unsigned)pp.size();
     ctx->n_samples = 0;
-    ctx->event_bytes = ctx->n_events = 0;
+    ctx->event_bytes = ctx->n_events = ctx->n_gated = 0;
     ctx->timing = r433b_timing{};
     std::vector<unsigned> ook = slice_list(ctx->devs, 1), fsk = slice_list(ctx->devs, 2);
     ctx->n_ook = (unsigned)ook.size();
@@ -1160,7 +1227,10 @@ int r433b_process_pulses(r433b_ctx *ctx, r433b_pulses const *ps)
         std::vector<SlicerParams> sp(rates.size() * n_devs);
         std::vector<GroupRange> rg(rates.size());
         for (size_t g = 0; g < rates.size(); ++g) {
-            for (uint32_t i = 0; i < n_devs; ++i) sp[g * n_devs + i] = scale_device(ctx->devs[i], rates[g].rate);
+            for (uint32_t i = 0; i < n_devs; ++i) {
+                sp[g * n_devs + i] = scale_device(ctx->devs[i], rates[g].rate);
+                if (!ctx->gates.empty()) sp[g * n_devs + i].gate = ctx->gates[i].min_bits;
+            }
             rg[g] = GroupRange{};
             rg[g].pkg_begin = rates[g].begin;
             rg[g].pkg_end = rates[g].end;
@@ -1214,6 +1284,7 @@ int r433b_process_pulses(r433b_ctx *ctx, r433b_pulses const *ps)
         ctx->timing.total_ms = ctx->timing.slice_ms;
         ctx->event_bytes = cursor[0];
         ctx->n_events = cursor[1];
+        ctx->n_gated = cursor[3];
     }
     ctx->processed = true;
     return R433B_OK;

@@ -50,7 +50,7 @@ struct GroupRange {
     unsigned pkg_begin, pkg_end;
     unsigned pool_begin, pool_end;
     unsigned long long arena_begin, arena_end;
-    unsigned long long events_end;
+    unsigned long long events_end, gated_end;
     unsigned overflow;
     unsigned next; // k_slice work counter: next (package, device group) item of this range, relative to pkg_begin
 };
@@ -70,6 +70,7 @@ __global__ void k_mark(GroupRange *r, int which, unsigned const *counters, unsig
     } else {
         r->arena_end = cursor[0];
         r->events_end = cursor[1];
+        r->gated_end = cursor[3];
         r->overflow |= (unsigned)cursor[2] << 1;
     }
 }
@@ -86,7 +87,7 @@ struct SliceParams {
     r433b_pair *pairs;        // n_pkgs * n_devs, pre-zeroed
     uint8_t *arena;
     unsigned long long arena_cap;
-    unsigned long long *cursor; // [0] bytes reserved, [1] events, [2] overflow
+    unsigned long long *cursor; // [0] bytes reserved, [1] events stored, [2] overflow, [3] events dropped by a gate
     uint32_t *stage;            // stage_words per thread of the (fixed, ranged) grid, or nullptr
     unsigned stage_words;
 };
@@ -135,7 +136,7 @@ __global__ void __launch_bounds__(kSliceThreads, kSliceCtasPerSm) k_slice(SliceP
         unsigned const slot = g * 32 + lane;
         unsigned const dev = slot < n_list ? list[slot] : kNoDevice;
         bool const active = dev != kNoDevice;
-        unsigned bytes = 0, nev = 0;
+        unsigned bytes = 0, nev = 0, ng1 = 0, ngN = 0;
         unsigned long long off = 0;
         bool fits = false;
         SlicerParams sp;
@@ -152,14 +153,18 @@ __global__ void __launch_bounds__(kSliceThreads, kSliceCtasPerSm) k_slice(SliceP
                     if ((int)lane >= o) incl += v;
                 }
                 unsigned total = __shfl_sync(0xffffffffu, incl, 31);
-                unsigned evs = nev;
+                unsigned evs = nev, dropped = ng1 + ngN;
 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) evs += __shfl_xor_sync(0xffffffffu, evs, o);
+                for (int o = 16; o > 0; o >>= 1) {
+                    evs += __shfl_xor_sync(0xffffffffu, evs, o);
+                    dropped += __shfl_xor_sync(0xffffffffu, dropped, o);
+                }
                 unsigned long long wbase = 0;
                 if (lane == 0 && total) {
                     wbase = atomicAdd(p.cursor, (unsigned long long)total);
                     atomicAdd(p.cursor + 1, (unsigned long long)evs);
                 }
+                if (lane == 0 && dropped) atomicAdd(p.cursor + 3, (unsigned long long)dropped);
                 wbase = __shfl_sync(0xffffffffu, wbase, 0);
                 off = wbase + incl - bytes;
                 fits = off + bytes <= p.arena_cap;
@@ -184,13 +189,15 @@ __global__ void __launch_bounds__(kSliceThreads, kSliceCtasPerSm) k_slice(SliceP
             if (active && (pass == 0 || (bytes && fits))) {
                 EventWriter w;
                 if (pass)
-                    w.init(reinterpret_cast<uint32_t *>(p.arena + off), bytes / 4);
+                    w.init(reinterpret_cast<uint32_t *>(p.arena + off), bytes / 4, (unsigned)sp.gate);
                 else
-                    w.init(stage, stage_words);
+                    w.init(stage, stage_words, (unsigned)sp.gate);
                 slice_dispatch(pv, sp, w);
                 if (pass == 0) {
                     bytes = w.committed * 4;
                     nev = w.events;
+                    ng1 = w.gated1;
+                    ngN = w.gatedN;
                 }
             }
         }
@@ -199,6 +206,8 @@ __global__ void __launch_bounds__(kSliceThreads, kSliceCtasPerSm) k_slice(SliceP
             pr.offset = off;
             pr.bytes = bytes;
             pr.events = nev;
+            pr.gated_single = ng1;
+            pr.gated_multi = ngN;
             p.pairs[(size_t)pk * p.n_devs + dev] = pr;
         }
     }

@@ -56,7 +56,8 @@ struct SlicerParams {
     int s_short, s_long, s_reset, s_gap, s_sync, s_tol;
     float f_short, f_long; // 1/(width*samples_per_us) or 0
     unsigned priority;
-    int pad;
+    int gate; // decoder length gate (r433b_gate.min_bits): events with >= 1 row whose rows all hold fewer bits are
+              // counted, not stored; 0 = every event is stored
 };
 
 // ----------------------------------------------------------------------------- writer ----
@@ -92,13 +93,20 @@ struct EventWriter {
     unsigned row_hw;    // data words that hold something
     uint32_t acc;       // word being assembled (MSB first)
     bool dirty;         // row length was reset while its bytes stayed (50-row overflow path)
+    // decoder length gate: an event the decoder would turn down for its row lengths alone is
+    // counted instead of stored -- by row count, because many decoders look at num_rows first
+    unsigned gate;      // bits; 0 = off
+    unsigned max_bits;  // longest closed row of the current event
+    unsigned gated1, gatedN; // dropped events of one row / of several rows
 
-    R4_HD void init(uint32_t *o, unsigned region_words = 0)
+    R4_HD void init(uint32_t *o, unsigned region_words = 0, unsigned gate_bits = 0)
     {
         out = o;
         limit = region_words;
         pos = committed = 0;
         events = 0;
+        gate = gate_bits;
+        gated1 = gatedN = 0;
         reset_event();
     }
 
@@ -112,6 +120,7 @@ struct EventWriter {
         bits = syncs = row_hw = 0;
         acc = 0;
         dirty = false;
+        max_bits = 0;
     }
 
     R4_HD void put(unsigned at, uint32_t v)
@@ -204,6 +213,7 @@ struct EventWriter {
         first_row();
         if (free_row < (unsigned)kBbRows) {
             if (num_rows == 1) row0_bits = bits;
+            if (bits > max_bits) max_bits = bits;
             close_row();
             free_row++;
             // physical rows taken by spill-over sit between the old and the new last row
@@ -236,6 +246,11 @@ struct EventWriter {
         if (num_rows == 0) { // an empty buffer is still an event (e.g. nrzs): header only
             ev_start = pos;
             pos += 1;
+        } else if ((bits > max_bits ? bits : max_bits) < gate) {
+            // bits_per_row[] all below the decoder's gate: decode_fn would return the gate's code at once
+            if (num_rows == 1) gated1++; else gatedN++;
+            reset_event();
+            return;
         } else {
             close_row();
             if (dirty) { // only the last row can be: its data length travels in a trailer word

@@ -29,7 +29,8 @@ EXPORTS = ["r433b_create", "r433b_destroy", "r433b_last_error", "r433b_set_level
            "r433b_pulses_create", "r433b_pulses_destroy", "r433b_pulses_clear", "r433b_pulses_load_ook",
            "r433b_pulses_load_rfraw", "r433b_pulses_add", "r433b_pulses_count", "r433b_pulses_get", "r433b_process_pulses",
            "r433b_format_ook", "r433b_format_ook_header", "r433b_format_vcd", "r433b_format_vcd_header",
-           "r433b_dump_logic_u8"]
+           "r433b_dump_logic_u8", "r433b_set_gates", "r433b_get_gated",
+           "r433b_dispatch_r_devices_parallel"]
 
 
 def build(force=False, verbose=False):
@@ -72,13 +73,18 @@ PACKAGE_DTYPE = np.dtype([("stream", "<u4"), ("seq", "<u4"), ("type", "<i4"), ("
                           ("first_pair", "<u4")])
 assert PACKAGE_DTYPE.itemsize == C.sizeof(Package) == 72
 
-PAIR_DTYPE = np.dtype([("offset", "<u8"), ("bytes", "<u4"), ("events", "<u4")])
+PAIR_DTYPE = np.dtype([("offset", "<u8"), ("bytes", "<u4"), ("events", "<u4"), ("gated_single", "<u4"), ("gated_multi", "<u4")])
+assert PAIR_DTYPE.itemsize == 24
 
 
 class Results(C.Structure):
     _fields_ = [("n_packages", C.c_uint32), ("n_devices", C.c_uint32), ("packages", C.c_void_p),
                 ("pulse_pool", C.c_void_p), ("gap_pool", C.c_void_p), ("pairs", C.c_void_p), ("events", C.c_void_p),
-                ("event_bytes", C.c_uint64), ("n_events", C.c_uint64), ("n_samples", C.c_uint64)]
+                ("event_bytes", C.c_uint64), ("n_events", C.c_uint64), ("n_samples", C.c_uint64), ("n_gated", C.c_uint64)]
+
+
+class Gate(C.Structure):
+    _fields_ = [("min_bits", C.c_uint16), ("code_single", C.c_int8), ("code_multi", C.c_int8)]
 
 
 class Timing(C.Structure):
@@ -137,6 +143,10 @@ def load():
     L.r433b_package_file_pos.argtypes = [C.c_void_p, C.POINTER(Results), C.c_uint32]
     L.r433b_dispatch.argtypes = [C.c_void_p, C.POINTER(Results), C.c_uint32, EVENT_FN, C.c_void_p]
     L.r433b_dispatch_r_devices.argtypes = [C.c_void_p, C.POINTER(Results), C.c_uint32, C.c_void_p, C.c_uint32]
+    L.r433b_dispatch_r_devices_parallel.argtypes = [C.c_void_p, C.POINTER(Results), C.c_void_p, C.c_uint32, C.c_uint32]
+    L.r433b_set_gates.argtypes = [C.c_void_p, C.POINTER(Gate), C.c_uint32]
+    L.r433b_get_gated.restype = C.c_uint64
+    L.r433b_get_gated.argtypes = [C.c_void_p]
     L.r433b_pulses_create.restype = C.c_void_p
     L.r433b_pulses_destroy.argtypes = [C.c_void_p]
     L.r433b_pulses_clear.argtypes = [C.c_void_p]
@@ -163,6 +173,14 @@ def default_device_table(include_disabled=False):
     with open(os.path.join(HERE, "data", "devices_25.12.json")) as f:
         devs = json.load(f)["devices"]
     return [d for d in devs if include_disabled or d["disabled"] == 0]
+
+
+def default_gates(devs):
+    """[(min_bits, code_single, code_multi)] for a device table: the length gates tools/probe_gates.py derived from
+    the reference's decoders (rtl_433_b200/data/gates_25.12.json); devices without an entry get no gate."""
+    with open(os.path.join(HERE, "data", "gates_25.12.json")) as f:
+        g = json.load(f)["gates"]
+    return [tuple(g.get(str(d.get("protocol_num", -1)), (0, 0, 0))) for d in devs]
 
 
 class R433Error(RuntimeError):
@@ -306,6 +324,18 @@ class Context:
         self._check(self.L.r433b_set_devices(self.h, arr, len(devs)))
         self.n_devices = len(devs)
 
+    def set_gates(self, gates):
+        """gates: [(min_bits, code_single, code_multi)] per device, or None / [] to clear (include/r433b.h: r433b_gate)."""
+        gates = gates or []
+        arr = (Gate * max(1, len(gates)))()
+        for i, g in enumerate(gates):
+            arr[i] = Gate(*g)
+        self._check(self.L.r433b_set_gates(self.h, arr, len(gates)))
+        self.gates = list(gates)
+
+    def gated(self):
+        return int(self.L.r433b_get_gated(self.h))
+
     def process(self, data, offsets, sample_format, samp_rate=250000, center_frequency=433920000, fpdm_mode=FPDM_AUTO,
                 block_bytes=0, data_on_device=False, want_stages=False, lengths=None):
         """`data`: host numpy array (any dtype, contiguous) or an int device pointer."""
@@ -353,9 +383,9 @@ class Context:
         pool_n = int((pk["pulse_off"].astype(np.int64) + pk["pulse_count"]).max()) if npk else 0
         return {"n_packages": npk, "n_devices": r.n_devices, "packages": pk,
                 "pulse_pool": view(r.pulse_pool, pool_n * 4, np.int32), "gap_pool": view(r.gap_pool, pool_n * 4, np.int32),
-                "pairs": view(r.pairs, npk * r.n_devices * 16, PAIR_DTYPE).reshape(npk, r.n_devices) if npk and r.n_devices else np.zeros((0, 0), PAIR_DTYPE),
+                "pairs": view(r.pairs, npk * r.n_devices * 24, PAIR_DTYPE).reshape(npk, r.n_devices) if npk and r.n_devices else np.zeros((0, 0), PAIR_DTYPE),
                 "events": view(r.events, r.event_bytes, np.uint8), "event_bytes": r.event_bytes, "n_events": r.n_events,
-                "n_samples": r.n_samples}
+                "n_samples": r.n_samples, "n_gated": r.n_gated}
 
     def stream_digest(self, stream):
         """Position-independent checksum of everything the fetched batch holds for one stream."""

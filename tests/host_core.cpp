@@ -323,7 +323,11 @@ int hc_collect_cb(void *user, uint32_t package, uint32_t device, struct pulse_da
     hc_event e;
     e.package = package;
     e.dev = device;
-    e.ret = 0;
+    // the shape a decoder length gate looks at: row count and the longest row (tests of r433b_set_gates)
+    unsigned longest = 0;
+    for (unsigned r = 0; r < bits->num_rows && r < R433B_BITBUF_ROWS; ++r)
+        if (bits->bits_per_row[r] > longest) longest = bits->bits_per_row[r];
+    e.ret = (int32_t)(((unsigned)bits->num_rows << 16) | longest);
     e.hash = fnv1a(bits, sizeof(*bits));
     e.bb_idx = 0xffffffffu;
     if (c->store) {

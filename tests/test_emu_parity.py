@@ -59,3 +59,16 @@ def test_emu_reverse_schedule(devices):
             "sys.exit(1 if bad else 0)") % (os.path.dirname(os.path.abspath(__file__)), emu.ROOT)
     env = dict(os.environ, SIMT_REVERSE="1")
     assert subprocess.call([sys.executable, "-c", code], env=env) == 0
+
+
+import test_gates  # noqa: E402
+
+
+def test_emu_gated_run_is_the_filtered_ungated_run():
+    """Decoder length gates in k_slice under the emulator: the body of the -m gpu test."""
+    test_gates.gated_run_is_the_filtered_ungated_run()
+
+
+@test_gates.needs_ref
+def test_emu_decoders_behind_gates_and_threads():
+    test_gates.decoders_behind_gates_and_threads()
