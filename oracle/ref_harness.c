@@ -829,3 +829,49 @@ REFH_EXPORT int refh_call_decoder(refh_t *h, int idx, bitbuffer_t const *bb, int
     g_active = saved;
     return ret;
 }
+
+/* -------- pulse analyzer of the reference (src/pulse_analyzer.c), SURVEY 8(f3) -------- */
+#include <unistd.h>
+#include <fcntl.h>
+#include "pulse_analyzer.h"
+
+/* pulse_analyzer() on a copy of `pd`; everything it prints to stderr goes to `buf`, the events of its trial
+   demodulation are captured like any others (device index -1).  Returns the text length. */
+REFH_EXPORT size_t refh_analyze(refh_t *h, pulse_data_t const *pd, int package_type, char *buf, size_t cap)
+{
+    static pulse_data_t work;
+    work = *pd;
+    clear_results(h);
+    g_active = h;
+    h->pkgs = grow(h->pkgs, &h->cap_pkgs, 1, sizeof(*h->pkgs));
+    memset(&h->pkgs[0], 0, sizeof(h->pkgs[0]));
+    h->n_pkgs = 1;
+    r_device device;
+    memset(&device, 0, sizeof(device));
+    device.log_fn = sink_log;
+    device.decode_fn = capture_cb;
+    char path[] = "/tmp/refh_analyze_XXXXXX";
+    int tmp = mkstemp(path);
+    if (tmp < 0) return 0;
+    fflush(stderr);
+    int saved = dup(2);
+    dup2(tmp, 2);
+    pulse_analyzer(&work, package_type, &device);
+    fflush(stderr);
+    dup2(saved, 2);
+    close(saved);
+    off_t len = lseek(tmp, 0, SEEK_END);
+    lseek(tmp, 0, SEEK_SET);
+    size_t n = (size_t)len < cap - 1 ? (size_t)len : cap - 1;
+    size_t got = 0;
+    while (got < n) {
+        ssize_t r = read(tmp, buf + got, n - got);
+        if (r <= 0) break;
+        got += (size_t)r;
+    }
+    buf[got] = 0;
+    close(tmp);
+    unlink(path);
+    g_active = NULL;
+    return (size_t)len;
+}

@@ -120,6 +120,8 @@ def lib():
         L.refh_dump_vcd.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_char_p, C.c_size_t]
         L.refh_dump_raw.argtypes = [C.c_void_p, C.c_uint, C.c_uint64, C.c_void_p, C.c_uint8]
         L.refh_slice_pulse_data.argtypes = [C.c_void_p, C.c_void_p]
+        L.refh_analyze.restype = C.c_size_t
+        L.refh_analyze.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_char_p, C.c_size_t]
         _lib = L
     return _lib
 
@@ -343,3 +345,16 @@ def _slice_pulse_data(self, pd):
 
 
 Ref.slice_pulse_data = _slice_pulse_data
+
+
+def _analyze(self, pd, package_type=1):
+    """pulse_analyzer() (src/pulse_analyzer.c:279) on a pulse_data_t record -> (stderr text, [bitbuffer hashes of
+    the trial demodulation's events])."""
+    pd = np.ascontiguousarray(pd).copy()
+    buf = C.create_string_buffer(1 << 18)
+    n = self.L.refh_analyze(self.h, pd.ctypes.data, package_type, buf, len(buf))
+    ev = self.L.refh_events(self.h)
+    return buf.raw[:n].decode(), [ev[i].hash for i in range(self.L.refh_num_events(self.h))]
+
+
+Ref.analyze = _analyze

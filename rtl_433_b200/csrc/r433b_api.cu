@@ -17,6 +17,8 @@
 #include "r433b_kernels.cuh"
 #include "r433b_host.hpp"
 #include "r433b_pulses.hpp"
+#include "r433b_analyze.cuh"
+#include "r433b_analyze_host.hpp"
 
 using namespace r433b;
 
@@ -92,6 +94,16 @@ struct r433b_ctx {
     // r433b_package.end_pos is the index into this table
     bool pulse_mode = false;
     std::vector<PulseSet::Meta> pulse_meta;
+    // pulse analyzer (r433b_analyze): results in DEVICE package order; dev_index[i] = device position of the
+    // i-th package of the fetched (sorted) array
+    std::vector<uint32_t> dev_index;
+    bool analyzed = false;
+    std::vector<r433b_analysis> an;
+    std::vector<r433b_guess> an_guess;
+    std::vector<std::string> an_text;
+    std::vector<r433b_pair> an_pairs;
+    std::vector<uint8_t> an_events;
+    DevBuf d_an, d_an_dev, d_an_gap, d_an_pairs, d_an_arena;
 };
 
 struct r433b_pulses {
@@ -197,7 +209,8 @@ void r433b_destroy(r433b_ctx *ctx)
     cudaSetDevice(ctx->device);
     for (DevBuf *b : {&ctx->d_data, &ctx->d_offsets, &ctx->d_train, &ctx->d_pkgs, &ctx->d_ppool, &ctx->d_gpool,
                  &ctx->d_counters, &ctx->d_am, &ctx->d_fm, &ctx->d_devparams, &ctx->d_lists, &ctx->d_pairs,
-                 &ctx->d_arena, &ctx->d_cursor, &ctx->d_ranges, &ctx->d_state, &ctx->d_lengths, &ctx->d_stage, &ctx->d_raw, &ctx->d_log, &ctx->d_amoff, &ctx->d_chunks})
+                 &ctx->d_arena, &ctx->d_cursor, &ctx->d_ranges, &ctx->d_state, &ctx->d_lengths, &ctx->d_stage, &ctx->d_raw, &ctx->d_log, &ctx->d_amoff, &ctx->d_chunks,
+                 &ctx->d_an, &ctx->d_an_dev, &ctx->d_an_gap, &ctx->d_an_pairs, &ctx->d_an_arena})
         if (b->p) cudaFree(b->p);
     for (HostBuf *b : {&ctx->h_pkgs, &ctx->h_ppool, &ctx->h_gpool, &ctx->h_pairs, &ctx->h_events, &ctx->h_ranges})
         if (b->p) cudaFreeHost(b->p);
@@ -797,10 +810,19 @@ int r433b_fetch(r433b_ctx *ctx, r433b_results *out)
     cudaEventElapsedTime(&ctx->timing.d2h_ms, ctx->ev[4], ctx->ev[5]);
     // the device wrote packages in completion order; the reference's order is per stream
     r433b_package *pk = (r433b_package *)ctx->h_pkgs.p;
-    if (!ctx->fetched)
-        std::sort(pk, pk + ctx->n_pkgs, [](r433b_package const &a, r433b_package const &b) {
-            return a.stream != b.stream ? a.stream < b.stream : a.seq < b.seq;
+    if (!ctx->fetched) {
+        // sort an index, then permute: dev_index remembers where each package sits on the device (r433b_analyze)
+        std::vector<uint32_t> &ix = ctx->dev_index;
+        ix.resize(ctx->n_pkgs);
+        for (uint32_t i = 0; i < ctx->n_pkgs; ++i) ix[i] = i;
+        std::sort(ix.begin(), ix.end(), [pk](uint32_t a, uint32_t b) {
+            return pk[a].stream != pk[b].stream ? pk[a].stream < pk[b].stream : pk[a].seq < pk[b].seq;
         });
+        std::vector<r433b_package> sorted(ctx->n_pkgs);
+        for (uint32_t i = 0; i < ctx->n_pkgs; ++i) sorted[i] = pk[ix[i]];
+        if (ctx->n_pkgs) memcpy(pk, sorted.data(), (size_t)ctx->n_pkgs * sizeof(r433b_package));
+        ctx->analyzed = false;
+    }
     ctx->fetched = true;
     out->n_packages = ctx->n_pkgs;
     out->n_devices = n_devs;
@@ -1211,10 +1233,16 @@ int r433b_process_pulses(r433b_ctx *ctx, r433b_pulses const *ps)
     std::vector<unsigned> ook = slice_list(ctx->devs, 1), fsk = slice_list(ctx->devs, 2);
     ctx->n_ook = (unsigned)ook.size();
     ctx->n_fsk = (unsigned)fsk.size();
-    if (n && n_devs) {
+    if (n) { // the packages and their widths go to the device even without devices (r433b_analyze needs them)
         if (int r = dev_reserve(ctx, ctx->d_pkgs, (size_t)n * sizeof(r433b_package))) return r;
         if (int r = dev_reserve(ctx, ctx->d_ppool, pp.size() * sizeof(int) + 16)) return r;
         if (int r = dev_reserve(ctx, ctx->d_gpool, gp.size() * sizeof(int) + 16)) return r;
+        CU(cudaMemcpyAsync(ctx->d_pkgs.p, hp.data(), (size_t)n * sizeof(r433b_package), cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(ctx->d_ppool.p, pp.data(), pp.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(ctx->d_gpool.p, gp.data(), gp.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+        CU(cudaStreamSynchronize(st));
+    }
+    if (n && n_devs) {
         size_t const pair_bytes = (size_t)n * n_devs * sizeof(r433b_pair);
         if (int r = dev_reserve(ctx, ctx->d_pairs, pair_bytes)) return r;
         if (int r = dev_reserve(ctx, ctx->d_ranges, rates.size() * sizeof(GroupRange))) return r;
@@ -1235,9 +1263,6 @@ int r433b_process_pulses(r433b_ctx *ctx, r433b_pulses const *ps)
             rg[g].pkg_begin = rates[g].begin;
             rg[g].pkg_end = rates[g].end;
         }
-        CU(cudaMemcpyAsync(ctx->d_pkgs.p, hp.data(), (size_t)n * sizeof(r433b_package), cudaMemcpyHostToDevice, st));
-        CU(cudaMemcpyAsync(ctx->d_ppool.p, pp.data(), pp.size() * sizeof(int), cudaMemcpyHostToDevice, st));
-        CU(cudaMemcpyAsync(ctx->d_gpool.p, gp.data(), gp.size() * sizeof(int), cudaMemcpyHostToDevice, st));
         CU(cudaMemcpyAsync(ctx->d_devparams.p, sp.data(), sp.size() * sizeof(SlicerParams), cudaMemcpyHostToDevice, st));
         if (!ook.empty()) CU(cudaMemcpyAsync(ctx->d_lists.p, ook.data(), ook.size() * sizeof(unsigned), cudaMemcpyHostToDevice, st));
         if (!fsk.empty())
@@ -1287,6 +1312,156 @@ int r433b_process_pulses(r433b_ctx *ctx, r433b_pulses const *ps)
         ctx->n_gated = cursor[3];
     }
     ctx->processed = true;
+    return R433B_OK;
+}
+
+} // extern "C"
+
+
+// ------------------------------------------------ pulse analyzer -------------
+
+namespace {
+
+uint32_t package_rate(r433b_ctx const *ctx, r433b_package const &k)
+{
+    if (ctx->pulse_mode && k.end_pos < ctx->pulse_meta.size()) return ctx->pulse_meta[k.end_pos].rate;
+    return ctx->batch.samp_rate;
+}
+
+} // namespace
+
+extern "C" {
+
+int r433b_analyze(r433b_ctx *ctx, r433b_results const *res)
+{
+    if (!ctx || !res) return R433B_EINVAL;
+    if (!ctx->fetched) return fail(ctx, R433B_ESTATE, "r433b_analyze before r433b_fetch");
+    CU(cudaSetDevice(ctx->device));
+    uint32_t const n = ctx->n_pkgs;
+    ctx->an.assign(n, r433b_analysis{});
+    ctx->an_guess.assign(n, r433b_guess{});
+    ctx->an_text.assign(n, std::string());
+    ctx->an_pairs.assign(n, r433b_pair{});
+    ctx->an_events.clear();
+    ctx->analyzed = true;
+    if (!n) return R433B_OK;
+    cudaStream_t const st = 0;
+    // 1. histograms on the GPU, device package order
+    if (int r = dev_reserve(ctx, ctx->d_an, (size_t)n * sizeof(r433b_analysis))) return r;
+    AnalyzeParams ap{};
+    ap.pkgs = (r433b_package const *)ctx->d_pkgs.p;
+    ap.n_pkgs = n;
+    ap.pulse_pool = (int const *)ctx->d_ppool.p;
+    ap.gap_pool = (int const *)ctx->d_gpool.p;
+    ap.out = (r433b_analysis *)ctx->d_an.p;
+    unsigned const grid = (unsigned)(((uint64_t)n * 5 + kAnalyzeThreads - 1) / kAnalyzeThreads);
+    R4_LAUNCH(k_analyze, grid, kAnalyzeThreads, 0, st, ap);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(ctx->an.data(), ctx->d_an.p, (size_t)n * sizeof(r433b_analysis), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    // 2. the guess and the text on the host (sorted package order -> device order through dev_index)
+    std::vector<SlicerParams> sp(n);
+    std::vector<int> last_gap(n, -1);
+    static thread_local struct pulse_data pd;
+    std::vector<char> buf(1 << 16);
+    bool any = false;
+    for (uint32_t i = 0; i < n; ++i) {
+        uint32_t const di = ctx->dev_index[i];
+        r433b_package_to_pulse_data(ctx, res, i, &pd);
+        r433b_guess g{};
+        size_t len = analysis_finish(&pd, res->packages[i].type, ctx->an[di], &g, buf.data(), buf.size());
+        if (len >= buf.size()) {
+            buf.resize(len + 1);
+            len = analysis_finish(&pd, res->packages[i].type, ctx->an[di], &g, buf.data(), buf.size());
+        }
+        ctx->an_text[di].assign(buf.data(), len);
+        ctx->an_guess[di] = g;
+        sp[di] = SlicerParams{};
+        if (g.modulation && g.sliced) {
+            r433b_device d{};
+            d.modulation = g.modulation;
+            d.short_width = g.short_width;
+            d.long_width = g.long_width;
+            d.reset_limit = g.reset_limit;
+            d.gap_limit = g.gap_limit;
+            d.sync_width = g.sync_width;
+            d.tolerance = g.tolerance;
+            sp[di] = scale_device(d, package_rate(ctx, res->packages[i]));
+            last_gap[di] = g.last_gap;
+            any = true;
+        }
+    }
+    if (!any) return R433B_OK;
+    // 3. the trial demodulation: every package through the slicer of its own guess
+    if (int r = dev_reserve(ctx, ctx->d_an_dev, (size_t)n * sizeof(SlicerParams))) return r;
+    if (int r = dev_reserve(ctx, ctx->d_an_gap, (size_t)n * sizeof(int))) return r;
+    if (int r = dev_reserve(ctx, ctx->d_an_pairs, (size_t)n * sizeof(r433b_pair))) return r;
+    CU(cudaMemcpyAsync(ctx->d_an_dev.p, sp.data(), (size_t)n * sizeof(SlicerParams), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(ctx->d_an_gap.p, last_gap.data(), (size_t)n * sizeof(int), cudaMemcpyHostToDevice, st));
+    CU(cudaMemsetAsync(ctx->d_an_pairs.p, 0, (size_t)n * sizeof(r433b_pair), st));
+    OwnSliceParams op{};
+    op.pkgs = ap.pkgs;
+    op.n_pkgs = n;
+    op.pulse_pool = ap.pulse_pool;
+    op.gap_pool = (int *)ctx->d_gpool.p;
+    op.dev = (SlicerParams const *)ctx->d_an_dev.p;
+    op.last_gap = (int const *)ctx->d_an_gap.p;
+    op.pairs = (r433b_pair *)ctx->d_an_pairs.p;
+    op.arena = nullptr;
+    op.pass = 0;
+    unsigned const og = (n + 127) / 128;
+    R4_LAUNCH(k_slice_own, og, 128, 0, st, op);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(ctx->an_pairs.data(), ctx->d_an_pairs.p, (size_t)n * sizeof(r433b_pair), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    uint64_t total = 0;
+    for (auto &pr : ctx->an_pairs) {
+        pr.offset = total;
+        total += pr.bytes;
+    }
+    if (total) {
+        if (int r = dev_reserve(ctx, ctx->d_an_arena, total)) return r;
+        CU(cudaMemcpyAsync(ctx->d_an_pairs.p, ctx->an_pairs.data(), (size_t)n * sizeof(r433b_pair), cudaMemcpyHostToDevice, st));
+        op.arena = (uint8_t *)ctx->d_an_arena.p;
+        op.pass = 1;
+        R4_LAUNCH(k_slice_own, og, 128, 0, st, op);
+        CU(cudaGetLastError());
+        ctx->an_events.resize(total);
+        CU(cudaMemcpyAsync(ctx->an_events.data(), ctx->d_an_arena.p, total, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+    }
+    return R433B_OK;
+}
+
+int r433b_analysis_get(r433b_ctx const *ctx, r433b_results const *res, uint32_t package, r433b_analysis *out, r433b_guess *guess)
+{
+    if (!ctx || !res || !ctx->analyzed || package >= ctx->dev_index.size()) return R433B_EINVAL;
+    uint32_t const di = ctx->dev_index[package];
+    if (out) *out = ctx->an[di];
+    if (guess) *guess = ctx->an_guess[di];
+    return R433B_OK;
+}
+
+size_t r433b_analysis_text(r433b_ctx const *ctx, r433b_results const *res, uint32_t package, char *buf, size_t cap)
+{
+    if (!ctx || !res || !ctx->analyzed || package >= ctx->dev_index.size()) return 0;
+    std::string const &t = ctx->an_text[ctx->dev_index[package]];
+    if (buf && cap) {
+        size_t n = t.size() < cap - 1 ? t.size() : cap - 1;
+        memcpy(buf, t.data(), n);
+        buf[n] = 0;
+    }
+    return t.size();
+}
+
+int r433b_analysis_events(r433b_ctx const *ctx, r433b_results const *res, uint32_t package, uint8_t const **events,
+        uint32_t *bytes, uint32_t *n_events)
+{
+    if (!ctx || !res || !ctx->analyzed || package >= ctx->dev_index.size()) return R433B_EINVAL;
+    r433b_pair const &pr = ctx->an_pairs[ctx->dev_index[package]];
+    if (events) *events = pr.bytes ? ctx->an_events.data() + pr.offset : nullptr;
+    if (bytes) *bytes = pr.bytes;
+    if (n_events) *n_events = pr.events;
     return R433B_OK;
 }
 

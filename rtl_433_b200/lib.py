@@ -30,7 +30,8 @@ EXPORTS = ["r433b_create", "r433b_destroy", "r433b_last_error", "r433b_set_level
            "r433b_pulses_load_rfraw", "r433b_pulses_add", "r433b_pulses_count", "r433b_pulses_get", "r433b_process_pulses",
            "r433b_format_ook", "r433b_format_ook_header", "r433b_format_vcd", "r433b_format_vcd_header",
            "r433b_dump_logic_u8", "r433b_set_gates", "r433b_get_gated",
-           "r433b_dispatch_r_devices_parallel"]
+           "r433b_dispatch_r_devices_parallel", "r433b_analyze", "r433b_analysis_get", "r433b_analysis_text",
+           "r433b_analysis_events"]
 
 
 def build(force=False, verbose=False):
@@ -81,6 +82,24 @@ class Results(C.Structure):
     _fields_ = [("n_packages", C.c_uint32), ("n_devices", C.c_uint32), ("packages", C.c_void_p),
                 ("pulse_pool", C.c_void_p), ("gap_pool", C.c_void_p), ("pairs", C.c_void_p), ("events", C.c_void_p),
                 ("event_bytes", C.c_uint64), ("n_events", C.c_uint64), ("n_samples", C.c_uint64), ("n_gated", C.c_uint64)]
+
+
+class HistBin(C.Structure):
+    _fields_ = [("count", C.c_uint32), ("sum", C.c_int32), ("mean", C.c_int32), ("min", C.c_int32), ("max", C.c_int32)]
+
+
+class Histogram(C.Structure):
+    _fields_ = [("bins_count", C.c_uint32), ("bins", HistBin * 16)]
+
+
+class Analysis(C.Structure):
+    _fields_ = [("hist", Histogram * 5), ("total_period", C.c_int32)]
+
+
+class Guess(C.Structure):
+    _fields_ = [("modulation", C.c_uint32), ("short_width", C.c_float), ("long_width", C.c_float), ("reset_limit", C.c_float),
+                ("gap_limit", C.c_float), ("sync_width", C.c_float), ("tolerance", C.c_float), ("last_gap", C.c_int32),
+                ("sliced", C.c_int32)]
 
 
 class Gate(C.Structure):
@@ -144,6 +163,12 @@ def load():
     L.r433b_dispatch.argtypes = [C.c_void_p, C.POINTER(Results), C.c_uint32, EVENT_FN, C.c_void_p]
     L.r433b_dispatch_r_devices.argtypes = [C.c_void_p, C.POINTER(Results), C.c_uint32, C.c_void_p, C.c_uint32]
     L.r433b_dispatch_r_devices_parallel.argtypes = [C.c_void_p, C.POINTER(Results), C.c_void_p, C.c_uint32, C.c_uint32]
+    L.r433b_analyze.argtypes = [C.c_void_p, C.POINTER(Results)]
+    L.r433b_analysis_get.argtypes = [C.c_void_p, C.POINTER(Results), C.c_uint32, C.POINTER(Analysis), C.POINTER(Guess)]
+    L.r433b_analysis_text.restype = C.c_size_t
+    L.r433b_analysis_text.argtypes = [C.c_void_p, C.POINTER(Results), C.c_uint32, C.c_char_p, C.c_size_t]
+    L.r433b_analysis_events.argtypes = [C.c_void_p, C.POINTER(Results), C.c_uint32, C.POINTER(C.c_void_p), C.POINTER(C.c_uint32),
+                                        C.POINTER(C.c_uint32)]
     L.r433b_set_gates.argtypes = [C.c_void_p, C.POINTER(Gate), C.c_uint32]
     L.r433b_get_gated.restype = C.c_uint64
     L.r433b_get_gated.argtypes = [C.c_void_p]
@@ -356,6 +381,29 @@ class Context:
         """All slicers on every package of a Pulses set (k_slice only); then fetch()/dispatch as usual."""
         self._keep = pulses
         self._check(self.L.r433b_process_pulses(self.h, pulses.h))
+
+    def analyze(self):
+        """The pulse analyzer (`rtl_433 -A`) on every package of the fetched batch."""
+        self._check(self.L.r433b_analyze(self.h, C.byref(self._res)))
+
+    def analysis(self, package_index):
+        """-> (Analysis, Guess, text, [bitbuffer records of the trial demodulation])"""
+        a, g = Analysis(), Guess()
+        self._check(self.L.r433b_analysis_get(self.h, C.byref(self._res), package_index, C.byref(a), C.byref(g)))
+        n = self.L.r433b_analysis_text(self.h, C.byref(self._res), package_index, None, 0)
+        buf = C.create_string_buffer(n + 1)
+        self.L.r433b_analysis_text(self.h, C.byref(self._res), package_index, buf, n + 1)
+        ev, nb, ne = C.c_void_p(), C.c_uint32(), C.c_uint32()
+        self._check(self.L.r433b_analysis_events(self.h, C.byref(self._res), package_index, C.byref(ev), C.byref(nb), C.byref(ne)))
+        bbs = np.zeros(ne.value, BITBUFFER_DTYPE)
+        at = 0
+        for i in range(ne.value):
+            used = C.c_uint32()
+            rc = self.L.r433b_event_to_bitbuffer(ev.value + at, nb.value - at, 0, bbs[i:i + 1].ctypes.data, C.byref(used))
+            if rc:
+                raise R433Error("corrupt analyzer event stream")
+            at += used.value
+        return a, g, buf.value.decode(), bbs
 
     def counts(self):
         out = (C.c_uint64 * 4)()

@@ -72,3 +72,12 @@ def test_emu_gated_run_is_the_filtered_ungated_run():
 @test_gates.needs_ref
 def test_emu_decoders_behind_gates_and_threads():
     test_gates.decoders_behind_gates_and_threads()
+
+
+import test_analyzer  # noqa: E402
+
+
+@test_analyzer.needs_ref
+def test_emu_analyzer_matches_the_reference():
+    """k_analyze / k_slice_own under the emulator: the body of the -m gpu test."""
+    test_analyzer.analyzer_matches_the_reference()
