@@ -875,3 +875,30 @@ REFH_EXPORT size_t refh_analyze(refh_t *h, pulse_data_t const *pd, int package_t
     g_active = NULL;
     return (size_t)len;
 }
+
+/* -------- SigMF container of the reference (src/sigmf.c), SURVEY 8(f2) -------- */
+#include "sigmf.h"
+
+/* sigmf_reader_open(): out = {rc, sample_rate, first_frequency, position of the stream after opening} -- the file
+   loop of src/rtl_433.c:1712-1723 then reads cu8 blocks from that position to the end of the archive */
+REFH_EXPORT void refh_sigmf_open(char const *path, uint64_t out[4])
+{
+    sigmf_t s;
+    memset(&s, 0, sizeof(s));
+    r_logger_set_log_handler(quiet_log, NULL);
+    fflush(stdout);
+    int saved = dup(1);
+    int nul = open("/dev/null", O_WRONLY);
+    dup2(nul, 1); /* json_parse() printf()s what it reads */
+    int rc = sigmf_reader_open(&s, path);
+    fflush(stdout);
+    dup2(saved, 1);
+    close(saved);
+    close(nul);
+    out[0] = (uint64_t)(int64_t)rc;
+    out[1] = s.sample_rate;
+    out[2] = s.first_frequency;
+    out[3] = s.mtar.stream ? (uint64_t)ftell(s.mtar.stream) : 0;
+    if (s.mtar.stream) fclose(s.mtar.stream);
+    sigmf_free_items(&s);
+}

@@ -120,6 +120,7 @@ def lib():
         L.refh_dump_vcd.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_char_p, C.c_size_t]
         L.refh_dump_raw.argtypes = [C.c_void_p, C.c_uint, C.c_uint64, C.c_void_p, C.c_uint8]
         L.refh_slice_pulse_data.argtypes = [C.c_void_p, C.c_void_p]
+        L.refh_sigmf_open.argtypes = [C.c_char_p, C.POINTER(C.c_uint64)]
         L.refh_analyze.restype = C.c_size_t
         L.refh_analyze.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_char_p, C.c_size_t]
         _lib = L
@@ -358,3 +359,11 @@ def _analyze(self, pd, package_type=1):
 
 
 Ref.analyze = _analyze
+
+
+def sigmf_open(path):
+    """sigmf_reader_open() -> dict(rc, sample_rate, center_frequency, data_offset)."""
+    out = (C.c_uint64 * 4)()
+    lib().refh_sigmf_open(path.encode(), out)
+    rc = out[0] if out[0] < (1 << 63) else out[0] - (1 << 64)
+    return {"rc": rc, "sample_rate": out[1], "center_frequency": out[2], "data_offset": out[3]}

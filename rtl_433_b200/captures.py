@@ -100,6 +100,60 @@ def parse_capture_name(spec):
     return info
 
 
+def read_sigmf(path):
+    """A SigMF archive as `rtl_433 -r x.sigmf` reads it (sigmf_reader_open(), src/sigmf.c:336-434, and the file loop
+    of src/rtl_433.c:1712-1723) -> dict(data, sample_rate, center_frequency, datatype, data_offset).
+
+    The first `.sigmf-meta` member names the stream; `global."core:sample_rate"` and the LAST capture's
+    `"core:frequency"` (src/sigmf.c:127-287 overwrites first_frequency per capture) become rate and centre
+    frequency; the samples are the member named like the meta file with `-data`.  Two properties of the reference
+    are kept because results depend on them: the payload is demodulated as cu8 whatever "core:datatype" says
+    (src/rtl_433.c:1719), and the block loop reads from the start of the data member to the END OF THE ARCHIVE,
+    i.e. including the tar padding and end-of-archive blocks behind the samples."""
+    import json
+
+    def members(raw):
+        # ustar walk like microtar's: 512-byte headers, octal size at 124, type flag at 156, all-zero block ends
+        pos = 0
+        while pos + 512 <= len(raw):
+            h = raw[pos:pos + 512]
+            if h[0] == 0:
+                break
+            name = h[:100].split(b"\0", 1)[0].decode("latin-1")
+            size = int(h[124:136].split(b"\0", 1)[0].strip() or b"0", 8)
+            kind = h[156:157]
+            yield name, size, kind, pos + 512
+            pos += 512 + (size + 511) // 512 * 512
+
+    raw = np.fromfile(path, dtype=np.uint8).tobytes()
+    stream, meta = None, None
+    for name, size, kind, at in members(raw):
+        if kind not in (b"0", b"\0"):
+            continue
+        if name.lower().endswith(".sigmf-meta"):
+            if stream is not None and name != stream:  # "updated meta file": the later stream name wins
+                stream, meta = None, None
+            if stream is None:
+                stream, meta = name, json.loads(raw[at:at + size].decode("utf-8", "replace") or "{}")
+    if stream is None:
+        raise ValueError(f"{path}: SigMF input file with no streams")
+    info = {"sample_rate": 0, "center_frequency": 0, "datatype": None}
+    g = meta.get("global", {}) if isinstance(meta, dict) else {}
+    if "core:sample_rate" in g:
+        info["sample_rate"] = int(float(g["core:sample_rate"])) & 0xffffffff
+    info["datatype"] = g.get("core:datatype")
+    for cap in meta.get("captures", []) if isinstance(meta, dict) else []:
+        if "core:frequency" in cap:
+            info["center_frequency"] = int(float(cap["core:frequency"])) & 0xffffffff
+    want = stream[:-4] + "data"
+    for name, size, kind, at in members(raw):
+        if name == want:
+            info["data_offset"] = at
+            info["data"] = np.frombuffer(raw, dtype=np.uint8)[at:].copy()
+            return info
+    raise ValueError(f"{path}: SigMF input file with no stream data")
+
+
 _ABI_FORMAT = {"cu8": lib.FMT_CU8, "cs8": lib.FMT_CS8, "cs16": lib.FMT_CS16, "cf32": lib.FMT_CF32}
 
 
@@ -107,8 +161,15 @@ def load_batches(specs, default_rate=DEFAULT_RATE, default_freq=DEFAULT_FREQ):
     """-> list of dict(format, sample_rate, center_frequency, files, data, offsets, lengths), one per
     (format, rate, frequency) group, files in command-line order inside a group."""
     groups = {}
+    preloaded = {}
     for spec in specs:
         info = parse_capture_name(spec)
+        if info["content"] == "sigmf":
+            # container: format, rate and frequency come from the archive's metadata, not from the name
+            sm = read_sigmf(info["path"])
+            preloaded[info["path"]] = sm["data"]
+            groups.setdefault(("cu8", sm["sample_rate"], sm["center_frequency"]), []).append(info["path"])
+            continue
         if info["format"] not in _ABI_FORMAT:
             raise ValueError(f"{spec}: format {info['format']!r} is not on the GPU path (cu8, cs8, cs16, cf32 are)")
         key = (info["format"], info["sample_rate"] or default_rate, info["center_frequency"] or default_freq)
@@ -117,7 +178,7 @@ def load_batches(specs, default_rate=DEFAULT_RATE, default_freq=DEFAULT_FREQ):
     for (fmt, rate, freq), paths in groups.items():
         ss = {"cu8": 2, "cs8": 2, "cs16": 4, "cf32": 8}[fmt]
         align = 32 if fmt == "cf32" else 16
-        bufs = [np.fromfile(p, dtype=np.uint8) for p in paths]
+        bufs = [preloaded[p] if p in preloaded else np.fromfile(p, dtype=np.uint8) for p in paths]
         lengths = np.array([len(b) // ss * ss for b in bufs], np.uint64)  # a trailing partial sample is dropped
         offsets = np.zeros(len(bufs) + 1, np.uint64)
         for i, n in enumerate(lengths):

@@ -94,7 +94,10 @@ struct SliceParams {
 
 constexpr int kSliceThreads = 128;
 constexpr unsigned kStageWords = 1024; // scratch words per k_slice thread (4 KiB): larger outputs take the second pass
-constexpr int kSliceCtasPerSm = 12; // 40 registers, 48 warps/SM (measured: 8 -> 13.3 ms, 10 -> 12.4, 12 -> 12.2, 16 -> 13.4)
+#ifndef R4_SLICE_CTAS
+#define R4_SLICE_CTAS 12
+#endif
+constexpr int kSliceCtasPerSm = R4_SLICE_CTAS; // 40 registers, 48 warps/SM (measured: 8 -> 13.3 ms, 10 -> 12.4, 12 -> 12.2, 16 -> 13.4)
 
 __global__ void __launch_bounds__(kSliceThreads, kSliceCtasPerSm) k_slice(SliceParams p)
 {

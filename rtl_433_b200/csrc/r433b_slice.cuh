@@ -672,40 +672,41 @@ R4_HD Step slicer_step(PulseView const &p, SlicerParams const &t, SlicerState &s
 }
 
 // ---- the shared back end.  Returns false when the slicer is finished (OSV1 after its event).
+// The 32 lanes of a warp are 32 devices that want different things from the writer at the same pulse; whatever
+// any lane wants is executed by the warp, so every writer primitive has ONE call site here and the lanes'
+// differences are predicates in front of it: a one bit and a zero bit are the same add_bits() with another value,
+// add_row / add_sync / "row if open" / "else row if open" are one add_row() with another condition.
 template <class W>
 R4_HD bool slicer_apply(Step const &s, W &w)
 {
-    if (s.ones) w.add_bits(1, s.ones);
-    if (s.zeros) w.add_bits(0, s.zeros);
-    if (s.row != kRowNone) {
-        if (s.row == kRowAdd)
-            w.add_row();
-        else if (s.row == kRowSync)
-            w.add_sync();
-        else if (s.row == kRowClear)
-            w.reset_event();
-        else if (w.num_rows > 0 && w.last_row_bits() > 0)
-            w.add_row();
+    // 1./2. the runs of bits: most slicers produce ones OR zeros per step (PCM and NRZS both, ones first)
+    {
+        int const first = s.ones ? s.ones : s.zeros;
+        if (first) w.add_bits(s.ones ? 1 : 0, first);
+        if (s.ones && s.zeros) w.add_bits(0, s.zeros);
     }
+    // 3. the row operation, and the one a step with kEmitElseRowIfOpen would do in 5.: never both (a row just
+    //    added is empty, which is what "if open" tests), and the steps that carry one of them have no `bit` in
+    //    between, so the second condition can be evaluated here
+    if (s.row == kRowAdd || s.row == kRowSync) w.first_row();
+    bool const open = w.num_rows > 0 && w.last_row_bits() > 0;
+    bool const want_row = s.row == kRowAdd || (s.row == kRowSync && w.last_row_bits() > 0)
+            || ((s.row == kRowIfOpen || s.emit == kEmitElseRowIfOpen) && open);
+    if (want_row) w.add_row();
+    if (s.row == kRowSync) w.syncs++; // bitbuffer_add_sync(): new row if the last one has bits, then count
+    if (s.row == kRowClear) w.reset_event();
+    // 4. single bit (Manchester's invalid-width path)
     if (s.bit) w.add_bits(s.bit - 1, 1);
-    bool emitted = false;
-    if (s.emit != kEmitNone) {
-        bool go;
-        if (s.emit == kEmitAlways) go = true;
-        else if (s.emit == kEmitIfRows) go = w.num_rows > 0;
-        else if (s.emit == kEmitIfData) go = w.first_row_bits() > 0 || w.num_rows > 1;
-        else if (s.emit == kEmitIfRow0) go = w.first_row_bits() > 0;
-        else {
-            go = false;
-            if (w.num_rows > 0 && w.last_row_bits() > 0) w.add_row();
-        }
-        if (go) {
-            w.emit();
-            emitted = true;
-        }
-    }
+    // 5. hand the event over?
+    bool go = false;
+    if (s.emit == kEmitAlways) go = true;
+    else if (s.emit == kEmitIfRows) go = w.num_rows > 0;
+    else if (s.emit == kEmitIfData) go = w.first_row_bits() > 0 || w.num_rows > 1;
+    else if (s.emit == kEmitIfRow0) go = w.first_row_bits() > 0;
+    if (go) w.emit();
     if (s.clear_after) w.reset_event();
-    if (emitted && s.stop_if_emitted) return false;
+    if (go && s.stop_if_emitted) return false;
+    // 6.
     if (s.post_zeros) w.add_bits(0, s.post_zeros);
     return true;
 }

@@ -71,3 +71,41 @@ def test_replay_files_on_gpu(tmp_path):
     want = o.run(files["silver_250k.cu8"], 2)
     got = [s for s in summary if s["file"] == paths[1]][0]
     assert got["packages"] == len(want["packages"]) and got["events"] == len(want["events"])
+
+
+def _make_sigmf(path, meta_name, meta, data, extra=()):
+    import io
+    import json
+    import tarfile
+    with tarfile.open(path, "w", format=tarfile.USTAR_FORMAT) as tar:
+        for name, payload in [(meta_name, json.dumps(meta).encode())] + list(extra) + [(meta_name[:-4] + "data", data)]:
+            ti = tarfile.TarInfo(name)
+            ti.size = len(payload)
+            tar.addfile(ti, io.BytesIO(payload))
+
+
+@pytest.mark.skipif(not refh.available(), reason="oracle/_ref not built")
+def test_sigmf_container_like_the_reference(tmp_path):
+    """rate / frequency / start of the sample data as sigmf_reader_open() finds them (src/sigmf.c:336-434)."""
+    x = synth.nice_flor_s_file()
+    meta = {"global": {"core:datatype": "cu8", "core:sample_rate": 250000, "core:version": "1.0.0", "core:recorder": "t"},
+            "captures": [{"core:sample_start": 0, "core:frequency": 433920000}, {"core:sample_start": 10, "core:frequency": 868300000.0}],
+            "annotations": []}
+    cases = []
+    p1 = str(tmp_path / "one.sigmf")
+    _make_sigmf(p1, "rec.sigmf-meta", meta, x.tobytes())
+    cases.append(p1)
+    p2 = str(tmp_path / "two_streams.sigmf")
+    m2 = dict(meta, **{"global": dict(meta["global"], **{"core:sample_rate": 1024000.0})})
+    _make_sigmf(p2, "dir/a.sigmf-meta", m2, x.tobytes()[:1000], extra=[("dir/readme.txt", b"hello" * 300)])
+    cases.append(p2)
+    for p in cases:
+        want = refh.sigmf_open(p)
+        got = captures.read_sigmf(p)
+        assert want["rc"] == 0
+        assert (got["sample_rate"], got["center_frequency"], got["data_offset"]) == (want["sample_rate"], want["center_frequency"], want["data_offset"])
+        raw = open(p, "rb").read()
+        assert got["data"].tobytes() == raw[want["data_offset"]:]  # the block loop reads to the end of the archive
+    b = captures.load_batches(["sigmf:" + p1, str(tmp_path / "missing_250k.cu8")][:1])
+    assert (b[0]["format"], b[0]["sample_rate"], b[0]["center_frequency"]) == ("cu8", 250000, 868300000)
+    assert bytes(b[0]["data"][:x.nbytes]) == x.tobytes()

@@ -112,7 +112,7 @@ def gated_run_is_the_filtered_ungated_run():
                     tgt[(e["package"], e["dev"])] = tgt.get((e["package"], e["dev"]), 0) + 1
                     dropped_total += 1
             for li, gi in enumerate(index):
-                row = res["pairs"][gi]
+                row = res["pairs"][int(pk["first_pair"][gi]) // res["n_devices"]]  # the pair table is in device order
                 for dv in np.nonzero(row["gated_single"] | row["gated_multi"])[0]:
                     assert int(row["gated_single"][dv]) == count1.get((li, int(dv)), 0)
                     assert int(row["gated_multi"][dv]) == countn.get((li, int(dv)), 0)

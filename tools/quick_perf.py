@@ -21,21 +21,29 @@ ap.add_argument("--fsk", action="store_true")
 ap.add_argument("--devices", default="all")
 ap.add_argument("--iters", type=int, default=3)
 ap.add_argument("--pipeline", type=int, default=0)
+ap.add_argument("--gates", action="store_true", help="decoder length gates on (r433b_set_gates)")
 ap.add_argument("--bursts", type=int, default=0, help="bursts per OOK stream (0 = synth default)")
 a = ap.parse_args()
 
 n = 1 << a.log2n
 t = time.time()
+cache = f"/tmp/qp_{'fsk' if a.fsk else 'ook'}_{a.distinct}_{a.log2n}_{a.bursts}.npy"
 if a.fsk:
-    base = [synth.fsk_stream(s, n_samples=n).view(np.uint8) for s in range(a.distinct)]
     fmt, rate, freq = lib.FMT_CS16, 1024000, 868000000
 else:
-    kw = {"n_bursts": a.bursts} if a.bursts else {}
-    base = [synth.ook_stream(s, n_samples=n, **kw) for s in range(a.distinct)]
     fmt, rate, freq = lib.FMT_CU8, 250000, 433920000
+if os.path.exists(cache):
+    host = np.load(cache)
+else:
+    if a.fsk:
+        base = [synth.fsk_stream(s, n_samples=n).view(np.uint8) for s in range(a.distinct)]
+    else:
+        kw = {"n_bursts": a.bursts} if a.bursts else {}
+        base = [synth.ook_stream(s, n_samples=n, **kw) for s in range(a.distinct)]
+    host = np.concatenate(base)
+    np.save(cache, host)
 print("generated", a.distinct, "streams in %.1fs" % (time.time() - t))
-per = base[0].nbytes
-host = np.concatenate(base)
+per = host.nbytes // a.distinct
 dev_small = torch.from_numpy(host).cuda()
 reps = (a.streams + a.distinct - 1) // a.distinct
 dev = dev_small.repeat(reps)[: a.streams * per].contiguous()
@@ -45,6 +53,8 @@ if a.devices != "all":
     devs = devs[: int(a.devices)]
 ctx = lib.Context(0)
 ctx.set_devices(devs)
+if a.gates:
+    ctx.set_gates(lib.default_gates(devs))
 ctx.set_pipeline(a.pipeline)
 import time as _t
 torch.cuda.synchronize()
