@@ -203,6 +203,13 @@ int r433b_dispatch(r433b_ctx *ctx, r433b_results const *res, uint32_t stream, r4
    exactly as account_event() does (src/pulse_slicer.c:26-66). */
 int r433b_dispatch_r_devices(r433b_ctx *ctx, r433b_results const *res, uint32_t stream,
         struct r_device *const *devs, uint32_t n);
+/* Asynchronous batches: r433b_process() + r433b_fetch() of `batch` on a worker thread of the context.  The descriptor
+   arrays are copied, the sample data must stay valid until r433b_wait().  One batch in flight per context, and the
+   context must not be used until it has been waited for.  To overlap the GPU with the host replay use two contexts
+   on one device alternately: submit(A, batch k+1); dispatch(results of B = batch k); wait(A); swap. */
+int r433b_submit(r433b_ctx *ctx, r433b_batch const *batch);
+int r433b_wait(r433b_ctx *ctx, r433b_results *out);
+
 /* Threaded replay: stream s is replayed by worker s % n_sets, each worker calling the decoders of its
    own set of r_device instances (dev_sets[w][0 .. n_devs): registered separately, so statistics and decoder contexts
    are per worker; one instance is never entered by two threads).  Order within a stream is the reference's.  The

@@ -157,9 +157,13 @@ def read_sigmf(path):
 _ABI_FORMAT = {"cu8": lib.FMT_CU8, "cs8": lib.FMT_CS8, "cs16": lib.FMT_CS16, "cf32": lib.FMT_CF32}
 
 
-def load_batches(specs, default_rate=DEFAULT_RATE, default_freq=DEFAULT_FREQ):
+def load_batches(specs, default_rate=DEFAULT_RATE, default_freq=DEFAULT_FREQ, uniform="auto"):
     """-> list of dict(format, sample_rate, center_frequency, files, data, offsets, lengths), one per
-    (format, rate, frequency) group, files in command-line order inside a group."""
+    (format, rate, frequency) group, files in command-line order inside a group.
+
+    `uniform`: put the files of a group on ONE stride (the longest file, rounded up) so that r433b_process() can
+    overlap the host-to-device copy with the kernels, time slice by time slice (one strided copy per slice);
+    "auto" does it when the padding costs less than half again the bytes, False packs the files back to back."""
     groups = {}
     preloaded = {}
     for spec in specs:
@@ -181,8 +185,12 @@ def load_batches(specs, default_rate=DEFAULT_RATE, default_freq=DEFAULT_FREQ):
         bufs = [preloaded[p] if p in preloaded else np.fromfile(p, dtype=np.uint8) for p in paths]
         lengths = np.array([len(b) // ss * ss for b in bufs], np.uint64)  # a trailing partial sample is dropped
         offsets = np.zeros(len(bufs) + 1, np.uint64)
-        for i, n in enumerate(lengths):
-            offsets[i + 1] = offsets[i] + (int(n) + align - 1) // align * align
+        longest = (int(lengths.max()) + 4095) // 4096 * 4096 if len(bufs) else 0
+        if uniform is True or (uniform == "auto" and len(bufs) > 1 and longest * len(bufs) <= 1.5 * float(lengths.sum())):
+            offsets = np.arange(len(bufs) + 1, dtype=np.uint64) * np.uint64(longest)
+        else:
+            for i, n in enumerate(lengths):
+                offsets[i + 1] = offsets[i] + (int(n) + align - 1) // align * align
         data = np.zeros(int(offsets[-1]), np.uint8)
         for i, b in enumerate(bufs):
             data[int(offsets[i]):int(offsets[i]) + int(lengths[i])] = b[:int(lengths[i])]

@@ -104,6 +104,13 @@ struct r433b_ctx {
     std::vector<r433b_pair> an_pairs;
     std::vector<uint8_t> an_events;
     DevBuf d_an, d_an_dev, d_an_gap, d_an_pairs, d_an_arena;
+    // r433b_submit / r433b_wait: one batch in flight on a worker thread
+    std::thread worker;
+    bool in_flight = false;
+    int worker_rc = 0;
+    r433b_batch sub_batch{};
+    std::vector<uint64_t> sub_offsets, sub_lengths;
+    r433b_results sub_res{};
 };
 
 struct r433b_pulses {
@@ -206,6 +213,7 @@ int r433b_create(int cuda_device, r433b_ctx **out)
 void r433b_destroy(r433b_ctx *ctx)
 {
     if (!ctx) return;
+    if (ctx->worker.joinable()) ctx->worker.join();
     cudaSetDevice(ctx->device);
     for (DevBuf *b : {&ctx->d_data, &ctx->d_offsets, &ctx->d_train, &ctx->d_pkgs, &ctx->d_ppool, &ctx->d_gpool,
                  &ctx->d_counters, &ctx->d_am, &ctx->d_fm, &ctx->d_devparams, &ctx->d_lists, &ctx->d_pairs,
@@ -509,8 +517,10 @@ int r433b_process(r433b_ctx *ctx, r433b_batch const *b)
     int G = ctx->pipeline_groups;
     uint64_t stride = b->n_streams ? ctx->offsets[1] - ctx->offsets[0] : 0;
     bool uniform = b->n_streams > 0 && stride > 0;
+    // one strided copy per time slice needs the streams on a uniform stride; their LENGTHS may differ (capture files of
+    // different sizes padded to a common stride): the kernels stop at every stream's own end
     for (uint32_t i = 0; uniform && i < b->n_streams; ++i)
-        if (ctx->offsets[i + 1] - ctx->offsets[i] != stride || ctx->lengths[i] != stride) uniform = false;
+        if (ctx->offsets[i + 1] - ctx->offsets[i] != stride) uniform = false;
     if (G == 0) // measured on B200 (tools/e2e_sweep.py): many slices of >= 128 KiB per stream beat fewer, larger ones
         G = (total_bytes >= (256ull << 20) && stride >= (1u << 20)) ? (int)std::min<uint64_t>(r433b_ctx::kMaxGroups, stride / (128u << 10)) : 1;
     if (b->data_on_device && ctx->pipeline_groups == 0) G = 1; // device input: slices only when asked for
@@ -1463,6 +1473,49 @@ int r433b_analysis_events(r433b_ctx const *ctx, r433b_results const *res, uint32
     if (bytes) *bytes = pr.bytes;
     if (n_events) *n_events = pr.events;
     return R433B_OK;
+}
+
+} // extern "C"
+
+
+// ------------------------------------------------ asynchronous batches -
+
+extern "C" {
+
+// r433b_process() + r433b_fetch() of `batch` on a worker thread of the context.  The descriptor arrays are copied,
+// the sample data is not: it must stay valid until r433b_wait().  One batch in flight per context; until it has
+// been waited for, the context must not be touched (the previous batch's results are overwritten while it runs).
+// The way to overlap the GPU with the host replay is two contexts on the same device used alternately:
+//     submit(A, batch k+1);  dispatch(results of B = batch k);  wait(A);  swap(A, B)
+int r433b_submit(r433b_ctx *ctx, r433b_batch const *batch)
+{
+    if (!ctx || !batch || !batch->offsets) return fail(ctx, R433B_EINVAL, "null argument");
+    if (ctx->in_flight) return fail(ctx, R433B_ESTATE, "r433b_submit: a batch is already in flight (r433b_wait first)");
+    if (ctx->worker.joinable()) ctx->worker.join();
+    ctx->sub_batch = *batch;
+    ctx->sub_offsets.assign(batch->offsets, batch->offsets + batch->n_streams + 1);
+    ctx->sub_batch.offsets = ctx->sub_offsets.data();
+    if (batch->lengths) {
+        ctx->sub_lengths.assign(batch->lengths, batch->lengths + batch->n_streams);
+        ctx->sub_batch.lengths = ctx->sub_lengths.data();
+    }
+    ctx->in_flight = true;
+    ctx->worker = std::thread([ctx]() {
+        int rc = r433b_process(ctx, &ctx->sub_batch);
+        if (!rc) rc = r433b_fetch(ctx, &ctx->sub_res);
+        ctx->worker_rc = rc;
+    });
+    return R433B_OK;
+}
+
+int r433b_wait(r433b_ctx *ctx, r433b_results *out)
+{
+    if (!ctx) return R433B_EINVAL;
+    if (!ctx->in_flight) return fail(ctx, R433B_ESTATE, "r433b_wait without r433b_submit");
+    ctx->worker.join();
+    ctx->in_flight = false;
+    if (!ctx->worker_rc && out) *out = ctx->sub_res;
+    return ctx->worker_rc;
 }
 
 } // extern "C"

@@ -31,7 +31,7 @@ EXPORTS = ["r433b_create", "r433b_destroy", "r433b_last_error", "r433b_set_level
            "r433b_format_ook", "r433b_format_ook_header", "r433b_format_vcd", "r433b_format_vcd_header",
            "r433b_dump_logic_u8", "r433b_set_gates", "r433b_get_gated",
            "r433b_dispatch_r_devices_parallel", "r433b_analyze", "r433b_analysis_get", "r433b_analysis_text",
-           "r433b_analysis_events"]
+           "r433b_analysis_events", "r433b_submit", "r433b_wait"]
 
 
 def build(force=False, verbose=False):
@@ -163,6 +163,8 @@ def load():
     L.r433b_dispatch.argtypes = [C.c_void_p, C.POINTER(Results), C.c_uint32, EVENT_FN, C.c_void_p]
     L.r433b_dispatch_r_devices.argtypes = [C.c_void_p, C.POINTER(Results), C.c_uint32, C.c_void_p, C.c_uint32]
     L.r433b_dispatch_r_devices_parallel.argtypes = [C.c_void_p, C.POINTER(Results), C.c_void_p, C.c_uint32, C.c_uint32]
+    L.r433b_submit.argtypes = [C.c_void_p, C.POINTER(Batch)]
+    L.r433b_wait.argtypes = [C.c_void_p, C.POINTER(Results)]
     L.r433b_analyze.argtypes = [C.c_void_p, C.POINTER(Results)]
     L.r433b_analysis_get.argtypes = [C.c_void_p, C.POINTER(Results), C.c_uint32, C.POINTER(Analysis), C.POINTER(Guess)]
     L.r433b_analysis_text.restype = C.c_size_t
@@ -405,6 +407,28 @@ class Context:
             at += used.value
         return a, g, buf.value.decode(), bbs
 
+    def submit(self, data, offsets, sample_format, samp_rate=250000, center_frequency=433920000, fpdm_mode=FPDM_AUTO,
+               block_bytes=0, data_on_device=False, lengths=None):
+        """process() + fetch() on the context's worker thread; wait() returns what fetch() would."""
+        offs = np.ascontiguousarray(offsets, dtype=np.uint64)
+        if isinstance(data, int):
+            ptr = data
+        else:
+            data = np.ascontiguousarray(data)
+            ptr = data.ctypes.data
+        lens = None if lengths is None else np.ascontiguousarray(lengths, dtype=np.uint64)
+        b = Batch(ptr, offs.ctypes.data_as(C.POINTER(C.c_uint64)), len(offs) - 1, sample_format, samp_rate,
+                  center_frequency, fpdm_mode, block_bytes, int(data_on_device), 0,
+                  None if lens is None else lens.ctypes.data_as(C.POINTER(C.c_uint64)))
+        self._keep = (data, offs, lens)
+        self._check(self.L.r433b_submit(self.h, C.byref(b)))
+
+    def wait(self):
+        r = Results()
+        self._check(self.L.r433b_wait(self.h, C.byref(r)))
+        self._res = r
+        return self._results_dict(r)
+
     def counts(self):
         out = (C.c_uint64 * 4)()
         self._check(self.L.r433b_get_counts(self.h, out))
@@ -420,7 +444,10 @@ class Context:
         r = Results()
         self._check(self.L.r433b_fetch(self.h, C.byref(r)))
         self._res = r
+        return self._results_dict(r)
 
+    @staticmethod
+    def _results_dict(r):
         def view(ptr, nbytes, dtype):
             if not nbytes:
                 return np.zeros(0, dtype)

@@ -31,6 +31,7 @@ from test_gpu_parity import (ctx, devices,  # noqa: E402,F401  (fixtures)
                              test_fsk_train_overflow_shifts_the_pulse_train,
                              test_magnitude_mode_and_fixed_level, test_ook_1200_pulse_end_of_package,
                              test_ook_cu8_default_devices, test_pipelined_time_slices_identical,
+                             test_pipelined_ragged_files_on_a_uniform_stride,
                              test_priority_classes_stop_after_a_decode, test_ragged_lengths_and_small_blocks,
                              test_rates_and_formats_round_1_never_compared, test_silence_and_reference_vectors)
 import test_pulse_io  # noqa: E402
@@ -81,3 +82,7 @@ import test_analyzer  # noqa: E402
 def test_emu_analyzer_matches_the_reference():
     """k_analyze / k_slice_own under the emulator: the body of the -m gpu test."""
     test_analyzer.analyzer_matches_the_reference()
+
+
+def test_emu_submit_wait_ping_pong():
+    test_gates.submit_wait_ping_pong()

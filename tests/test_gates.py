@@ -211,3 +211,46 @@ def decoders_behind_gates_and_threads():
 @needs_ref
 def test_decoders_behind_gates_and_threads():
     decoders_behind_gates_and_threads()
+
+
+def submit_wait_ping_pong():
+    """Two contexts used alternately (r433b_submit / r433b_wait): batch k+1 is processed on a worker thread while the
+    caller replays batch k; results equal those of plain process() + fetch()."""
+    devices = lib.default_device_table()
+    batches = [np.concatenate([synth.ook_stream(80 + 2 * k, n_samples=1 << 18, n_bursts=3),
+                               synth.ook_stream(81 + 2 * k, n_samples=1 << 18, n_bursts=3)]) for k in range(3)]
+    offs = np.array([0, batches[0].nbytes // 2, batches[0].nbytes], np.uint64)
+    ctxs = [lib.Context(0), lib.Context(0)]
+    try:
+        want = []
+        for c in ctxs:
+            c.set_devices(devices)
+            c.set_gates(lib.default_gates(devices))
+        for b in batches:
+            ctxs[0].process(b, offs, lib.FMT_CU8, 250000, 433920000)
+            ctxs[0].fetch()
+            want.append([ctxs[0].stream_digest(s) for s in range(2)])
+        got = []
+        ctxs[0].submit(batches[0], offs, lib.FMT_CU8, 250000, 433920000)
+        for k in range(len(batches)):
+            cur, nxt = ctxs[k % 2], ctxs[(k + 1) % 2]
+            res = cur.wait()
+            if k + 1 < len(batches):
+                nxt.submit(batches[k + 1], offs, lib.FMT_CU8, 250000, 433920000)  # runs while batch k is replayed below
+            assert res["n_packages"] >= 6
+            events = []
+            for s in range(2):
+                cur.dispatch(s, lambda pk, dv, pd, bb: events.append(dv) or 0)
+            assert len(events) == res["n_events"]
+            got.append([cur.stream_digest(s) for s in range(2)])
+        assert got == want
+        with pytest.raises(lib.R433Error):
+            ctxs[0].wait()
+    finally:
+        for c in ctxs:
+            c.close()
+
+
+@pytest.mark.gpu
+def test_submit_wait_ping_pong():
+    submit_wait_ping_pong()

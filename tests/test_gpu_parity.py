@@ -207,6 +207,34 @@ def test_pipelined_time_slices_identical(ctx, devices):
         ctx.set_pipeline(0)
 
 
+def test_pipelined_ragged_files_on_a_uniform_stride(ctx, devices):
+    """Capture files of different lengths padded to a common stride (captures.load_batches(uniform=True)) take the
+    pipelined host path too: every stream ends -- and is flushed -- in the time slice that reaches its own end."""
+    full = [synth.ook_stream(70 + seed, n_samples=1 << 19, n_bursts=4) for seed in range(5)]
+    cuts = [len(full[0]), 2 * 16 * 20011, 2 * 131072 * 2, 2 * 16 * 9, 2 * (131072 * 3 + 16 * 77)]
+    streams = [s[:c] for s, c in zip(full, cuts)]
+    o = oracle_for(devices, stages=False)
+    refs = [o.run(s, 2) for s in streams]
+    stride = len(full[0])
+    data = np.full(stride * len(streams), 0x5a, np.uint8)  # bytes behind a file's end must never be looked at
+    for i, s in enumerate(streams):
+        data[i * stride:i * stride + len(s)] = s
+    offsets = np.arange(len(streams) + 1, dtype=np.uint64) * np.uint64(stride)
+    lengths = np.array([len(s) for s in streams], np.uint64)
+    try:
+        for groups in (4, 16):
+            ctx.set_pipeline(groups)
+            ctx.process(data, offsets, lib.FMT_CU8, 250000, 433920000, lengths=lengths)
+            ctx.fetch()
+            assert ctx.timing()["detect_launches"] > 1
+            for i in range(len(streams)):
+                got = helpers.gpu_stream_results(ctx, i)
+                d = helpers.compare_results(refs[i], got, f"ragged pipeline {groups} stream {i}", stages=False)
+                assert not d, "\n".join(d[:20])
+    finally:
+        ctx.set_pipeline(0)
+
+
 def test_cs8_input_is_cu8_plus_128(ctx, devices):
     """cs8 captures are converted to cu8 (+128, src/rtl_433.c:1830-1834) inside the load phase."""
     streams = [synth.ook_stream(31), synth.ook_stream(32)[: 2 * 16 * 40001]]
