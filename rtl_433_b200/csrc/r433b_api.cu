@@ -67,6 +67,7 @@ struct r433b_ctx {
     int n_sms = 148;        // cudaDevAttrMultiProcessorCount of `device`
     unsigned stage_words = kStageWords; // R433B_STAGE_WORDS overrides (tuning experiments)
     int spoil_front = 0; // R433B_SPOIL_FRONT=1|2: k_front starts from wrong guesses (tests of the redo / repair paths)
+    int slice_v2 = 1; // k_slice2 (lanes = packages of one device); R433B_SLICE_V1=1 selects k_slice (lanes = devices on one package)
     int lazy_fm = 1; // R433B_EAGER_FM=1 in the environment turns the on-demand FM path off (A/B checks)
     Levels lv{};
     // device memory (grow only)
@@ -86,6 +87,7 @@ struct r433b_ctx {
     cudaStream_t s_in = nullptr, s_det = nullptr, s_out = nullptr;
     static constexpr int kMaxGroups = 16;
     cudaEvent_t ev_in[kMaxGroups]{}, ev_det[kMaxGroups]{}, ev_slc[kMaxGroups]{}, ev_t[4 * kMaxGroups]{}, ev_f[kMaxGroups]{}, ev_init = nullptr;
+    DevBuf d_order; // k_bucket: package indices sorted by (type, length class), per range
     DevBuf d_ranges, d_state, d_lengths, d_stage, d_raw, d_log, d_amoff, d_chunks;
     std::vector<uint64_t> am_offsets; // first sample of stream i in d_am (multiples of the tile), n_streams + 1
     HostBuf h_ranges;
@@ -202,6 +204,7 @@ int r433b_create(int cuda_device, r433b_ctx **out)
     cudaEventCreateWithFlags(&ctx->ev_init, cudaEventDisableTiming);
     ctx->lv = compute_levels(0, 0.0f, -12.1442f, 9.0f);
     if (char const *v = getenv("R433B_EAGER_FM")) ctx->lazy_fm = !(v[0] && v[0] != '0');
+    if (char const *v = getenv("R433B_SLICE_V1")) ctx->slice_v2 = !(v[0] && v[0] != '0');
     if (char const *v = getenv("R433B_SPOIL_FRONT")) ctx->spoil_front = atoi(v);
     if (char const *v = getenv("R433B_STAGE_WORDS")) ctx->stage_words = (unsigned)std::max(8, atoi(v));
     if (cudaDeviceGetAttribute(&ctx->n_sms, cudaDevAttrMultiProcessorCount, cuda_device) != cudaSuccess || ctx->n_sms <= 0)
@@ -218,7 +221,7 @@ void r433b_destroy(r433b_ctx *ctx)
     for (DevBuf *b : {&ctx->d_data, &ctx->d_offsets, &ctx->d_train, &ctx->d_pkgs, &ctx->d_ppool, &ctx->d_gpool,
                  &ctx->d_counters, &ctx->d_am, &ctx->d_fm, &ctx->d_devparams, &ctx->d_lists, &ctx->d_pairs,
                  &ctx->d_arena, &ctx->d_cursor, &ctx->d_ranges, &ctx->d_state, &ctx->d_lengths, &ctx->d_stage, &ctx->d_raw, &ctx->d_log, &ctx->d_amoff, &ctx->d_chunks,
-                 &ctx->d_an, &ctx->d_an_dev, &ctx->d_an_gap, &ctx->d_an_pairs, &ctx->d_an_arena})
+                 &ctx->d_order, &ctx->d_an, &ctx->d_an_dev, &ctx->d_an_gap, &ctx->d_an_pairs, &ctx->d_an_arena})
         if (b->p) cudaFree(b->p);
     for (HostBuf *b : {&ctx->h_pkgs, &ctx->h_ppool, &ctx->h_gpool, &ctx->h_pairs, &ctx->h_events, &ctx->h_ranges})
         if (b->p) cudaFreeHost(b->p);
@@ -304,6 +307,27 @@ int r433b_set_r_devices(r433b_ctx *ctx, struct r_device *const *devs, uint32_t n
     }
     return R433B_OK;
 }
+
+namespace {
+
+// The slicers over one package range: k_bucket + k_slice2 (lanes = packages of one device), or k_slice.
+void launch_slice(r433b_ctx *ctx, SliceParams const &q, unsigned slice_grid, cudaStream_t st)
+{
+    if (ctx->slice_v2) {
+        Slice2Params q2{};
+        q2.s = q;
+        q2.order = (unsigned const *)ctx->d_order.p;
+        unsigned const bgrid = (unsigned)ctx->n_sms * 2;
+        R4_LAUNCH(k_bucket_count, bgrid, kBucketThreads, 0, st, q.range, q.pkgs, q.n_pkgs, q.n_devs);
+        R4_LAUNCH(k_bucket_scan, 1, 1, 0, st, q.range);
+        R4_LAUNCH(k_bucket_scatter, bgrid, kBucketThreads, 0, st, q.range, (r433b_package const *)q.pkgs, q.n_pkgs, (unsigned *)ctx->d_order.p);
+        R4_LAUNCH(k_slice2, slice_grid, kSliceThreads, 0, st, q2);
+    } else {
+        R4_LAUNCH(k_slice, slice_grid, kSliceThreads, 0, st, q);
+    }
+}
+
+} // namespace
 
 int r433b_process(r433b_ctx *ctx, r433b_batch const *b)
 {
@@ -538,6 +562,7 @@ int r433b_process(r433b_ctx *ctx, r433b_batch const *b)
         using clk = std::chrono::steady_clock;
         auto t_wall0 = clk::now();
         if (int r = dev_reserve(ctx, ctx->d_pkgs, ctx->pkg_cap * sizeof(r433b_package))) return r;
+        if (int r = dev_reserve(ctx, ctx->d_order, ctx->pkg_cap * sizeof(unsigned))) return r;
         if (int r = dev_reserve(ctx, ctx->d_ppool, ctx->pool_cap * sizeof(int))) return r;
         if (int r = dev_reserve(ctx, ctx->d_gpool, ctx->pool_cap * sizeof(int))) return r;
         size_t const pair_cap_bytes = ctx->pkg_cap * n_devs * sizeof(r433b_pair);
@@ -591,7 +616,7 @@ int r433b_process(r433b_ctx *ctx, r433b_batch const *b)
             CU(cudaEventRecord(ctx->ev_t[4 * g + 2], ctx->s_det));
             SliceParams qg = q;
             qg.range = d_rg + g;
-            R4_LAUNCH(k_slice, slice_grid, kSliceThreads, 0, ctx->s_det, qg);
+            launch_slice(ctx, qg, slice_grid, ctx->s_det);
             CU(cudaEventRecord(ctx->ev_t[4 * g + 3], ctx->s_det));
             R4_LAUNCH(k_mark, 1, 1, 0, ctx->s_det, d_rg + g, 3, d_cnt, d_cur);
             CU(cudaMemcpyAsync(h_rg + g, d_rg + g, sizeof(GroupRange), cudaMemcpyDeviceToHost, ctx->s_det));
@@ -724,6 +749,7 @@ int r433b_process(r433b_ctx *ctx, r433b_batch const *b)
     if (ctx->n_pkgs && n_devs) {
         size_t pair_bytes = (size_t)ctx->n_pkgs * n_devs * sizeof(r433b_pair);
         if (int r = dev_reserve(ctx, ctx->d_pairs, pair_bytes)) return r;
+        if (int r = dev_reserve(ctx, ctx->d_order, (size_t)ctx->n_pkgs * sizeof(unsigned))) return r;
         if (int r = dev_reserve(ctx, ctx->d_ranges, sizeof(GroupRange))) return r;
         for (int attempt = 0; attempt < 3; ++attempt) {
             if (int r = dev_reserve(ctx, ctx->d_arena, ctx->arena_cap)) return r;
@@ -736,7 +762,7 @@ int r433b_process(r433b_ctx *ctx, r433b_batch const *b)
             all.pkg_end = ctx->n_pkgs;
             CU(cudaMemcpyAsync(ctx->d_ranges.p, &all, sizeof(all), cudaMemcpyHostToDevice, st));
             q.range = (GroupRange *)ctx->d_ranges.p;
-            R4_LAUNCH(k_slice, slice_grid, kSliceThreads, 0, st, q);
+            launch_slice(ctx, q, slice_grid, st);
             CU(cudaGetLastError());
             slice_launches++;
             CU(cudaMemcpyAsync(cursor, ctx->d_cursor.p, sizeof(cursor), cudaMemcpyDeviceToHost, st));
@@ -1256,6 +1282,7 @@ int r433b_process_pulses(r433b_ctx *ctx, r433b_pulses const *ps)
         size_t const pair_bytes = (size_t)n * n_devs * sizeof(r433b_pair);
         if (int r = dev_reserve(ctx, ctx->d_pairs, pair_bytes)) return r;
         if (int r = dev_reserve(ctx, ctx->d_ranges, rates.size() * sizeof(GroupRange))) return r;
+        if (int r = dev_reserve(ctx, ctx->d_order, (size_t)n * sizeof(unsigned))) return r;
         if (int r = dev_reserve(ctx, ctx->d_devparams, rates.size() * n_devs * sizeof(SlicerParams))) return r;
         if (int r = dev_reserve(ctx, ctx->d_lists, (ook.size() + fsk.size() + 1) * sizeof(unsigned))) return r;
         if (int r = dev_reserve(ctx, ctx->d_cursor, 64)) return r;
@@ -1303,7 +1330,7 @@ int r433b_process_pulses(r433b_ctx *ctx, r433b_pulses const *ps)
                 q.cursor = (unsigned long long *)ctx->d_cursor.p;
                 q.stage = (uint32_t *)ctx->d_stage.p;
                 q.stage_words = ctx->stage_words;
-                R4_LAUNCH(k_slice, slice_grid, kSliceThreads, 0, st, q);
+                launch_slice(ctx, q, slice_grid, st);
                 CU(cudaGetLastError());
                 ctx->timing.slice_launches++;
             }

@@ -312,13 +312,27 @@ struct SlicerState {
     int since;             // MC: time since last edge; OSV1: manchester phase; RZI: fresh flag
     double edge;           // MC: 1.5 * s_short
     bool pending;          // OSV1: a zero bit owed before the first data pulse
+    int cv, cg;            // pulse[k], gap[k] of the per-pulse slicers, loaded one step ahead (slicer_advance)
 };
+
+// Move a per-pulse slicer to pulse `k` and issue the loads of its widths now: they are needed one whole step (the
+// front end's classification and the bit writer's work) later, so their latency -- every lane reads another package in
+// k_slice2 -- is off the critical path.
+R4_HD void slicer_advance(PulseView const &p, SlicerState &st, unsigned k)
+{
+    st.k = k;
+    if (k < st.total) {
+        st.cv = p.pulse[k];
+        st.cg = p.gap[k];
+    }
+}
 
 // ---- set-up: everything the reference does before its main loop; returns false if the slicer
 //      produces nothing (src/pulse_slicer.c, "check for rounding to zero" and early returns)
-R4_HD bool slicer_begin(PulseView const &p, SlicerParams const &t, SlicerState &st)
+R4_HD bool slicer_begin0(PulseView const &p, SlicerParams const &t, SlicerState &st)
 {
     st.k = 0;
+    st.cv = st.cg = 0;
     st.total = p.n;
     st.since = 0;
     st.pending = false;
@@ -487,6 +501,13 @@ R4_HD bool slicer_begin(PulseView const &p, SlicerParams const &t, SlicerState &
     }
 }
 
+R4_HD bool slicer_begin(PulseView const &p, SlicerParams const &t, SlicerState &st)
+{
+    if (!slicer_begin0(p, t, st)) return false;
+    slicer_advance(p, st, st.k); // widths of the first pulse the main loop looks at
+    return true;
+}
+
 // ---- one iteration of the main loop of the slicer -> what it does to the bit buffer
 R4_HD Step slicer_step(PulseView const &p, SlicerParams const &t, SlicerState &st)
 {
@@ -499,7 +520,7 @@ R4_HD Step slicer_step(PulseView const &p, SlicerParams const &t, SlicerState &s
     unsigned const n = st.k;
     switch (t.modulation) {
     case kModOokPwm: case kModFskPwm: { // src/pulse_slicer.c:415-447
-        int v = p.pulse[n], g = p.gap[n];
+        int v = st.cv, g = st.cg;
         if (v > st.b0 && v < st.b1) s.ones = 1;
         else if (v > st.b2 && v < st.b3) s.zeros = 1;
         else if (v > st.b4 && v < st.b5) s.row = kRowSync;
@@ -507,21 +528,21 @@ R4_HD Step slicer_step(PulseView const &p, SlicerParams const &t, SlicerState &s
         else s.row = kRowAdd;
         if (n == st.total - 1 || g > t.s_reset) s.emit = kEmitIfRows;
         else if (t.s_gap > 0 && g > t.s_gap) s.emit = kEmitElseRowIfOpen;
-        st.k = n + 1;
+        slicer_advance(p, st, n + 1);
         break;
     }
     case kModOokPpm: { // :310-335
-        int g = p.gap[n];
+        int g = st.cg;
         if (g > st.b0 && g < st.b1) s.zeros = 1;
         else if (g > st.b2 && g < st.b3) s.ones = 1;
         else if (g > st.b4 && g < st.b5) s.row = kRowSync;
         else if (g < t.s_reset) s.row = kRowAdd;
         if (n == st.total - 1 || g >= t.s_reset) s.emit = kEmitIfData;
-        st.k = n + 1;
+        slicer_advance(p, st, n + 1);
         break;
     }
     case kModOokPcm: case kModFskPcm: { // :216-257
-        int v = p.pulse[n], g = p.gap[n];
+        int v = st.cv, g = st.cg;
         int highs = (int)fadd(fmul((float)v, st.f_short), 0.5f);
         int lows = (int)fadd(fmul((float)(g + t.s_short - t.s_long), st.f_long), 0.5f);
         if (lows > st.i1) lows = st.i1;
@@ -530,7 +551,7 @@ R4_HD Step slicer_step(PulseView const &p, SlicerParams const &t, SlicerState &s
         if (t.s_short != t.s_long && iabs(v - t.s_short) > st.i2) s.row = kRowClear;
         else if (g > st.i0 && g <= t.s_reset) s.row = kRowAdd;
         if (n == st.total - 1 || g > t.s_reset) s.emit = kEmitIfData;
-        st.k = n + 1;
+        slicer_advance(p, st, n + 1);
         break;
     }
     case kModOokMc: case kModFskMc: { // :478-525; the buffer always holds >= 1 row here
@@ -539,7 +560,7 @@ R4_HD Step slicer_step(PulseView const &p, SlicerParams const &t, SlicerState &s
             s.zeros = 1;
             break;
         }
-        int v = p.pulse[n], g = p.gap[n];
+        int v = st.cv, g = st.cg;
         int const lo = st.i0, hi = st.i1;
         if (t.s_tol > 0 && (v < lo || v > hi || g < lo || g > hi)) {
             if ((double)v > st.edge && v <= hi) s.ones = 1;
@@ -562,7 +583,7 @@ R4_HD Step slicer_step(PulseView const &p, SlicerParams const &t, SlicerState &s
         } else {
             st.since += g;
         }
-        st.k = n + 1;
+        slicer_advance(p, st, n + 1);
         break;
     }
     case kModOokDmc: { // :562-592 (consumes a second symbol after a short one)
@@ -611,15 +632,15 @@ R4_HD Step slicer_step(PulseView const &p, SlicerParams const &t, SlicerState &s
         break;
     }
     case kModOokNrzs: { // :741-756
-        int v = p.pulse[n];
+        int v = st.cv;
         if (v > t.s_short) {
             s.ones = v / t.s_short;
             s.zeros = 1;
         } else if (v < t.s_short) {
             s.zeros = 1;
         }
-        if (n == st.total - 1 || p.gap[n] >= t.s_reset) s.emit = kEmitAlways;
-        st.k = n + 1;
+        if (n == st.total - 1 || st.cg >= t.s_reset) s.emit = kEmitAlways;
+        slicer_advance(p, st, n + 1);
         break;
     }
     case kModOokOsv1: { // :837-862
@@ -631,37 +652,37 @@ R4_HD Step slicer_step(PulseView const &p, SlicerParams const &t, SlicerState &s
         int man = st.since;
         man ^= 1;
         if (man) s.ones++;
-        if (p.pulse[n] > st.i0) {
+        if (st.cv > st.i0) {
             man ^= 1;
             if (man) s.ones++;
         }
-        if (n == st.total - 1 || p.gap[n] > t.s_reset) {
+        if (n == st.total - 1 || st.cg > t.s_reset) {
             s.emit = kEmitIfRows;
             s.stop_if_emitted = true;
         }
         man ^= 1;
         if (man) s.post_zeros++;
-        if (p.gap[n] > st.i0) {
+        if (st.cg > st.i0) {
             man ^= 1;
             if (man) s.post_zeros++;
         }
         st.since = man;
-        st.k = n + 1;
+        slicer_advance(p, st, n + 1);
         break;
     }
     case kModOokRzi: { // :887-915
-        int high = p.pulse[n];
+        int high = st.cv;
         int ones = st.since ? (high + t.s_long / 2) / t.s_long : (high - st.i0 + t.s_long / 2) / t.s_long;
         st.since = 0;
         s.ones = ones > 0 ? ones : 0;
-        if (p.gap[n] > t.s_reset || n == st.total - 1) {
+        if (st.cg > t.s_reset || n == st.total - 1) {
             s.emit = kEmitIfRow0;
             s.clear_after = true;
             st.since = 1;
         } else {
             s.post_zeros = 1;
         }
-        st.k = n + 1;
+        slicer_advance(p, st, n + 1);
         break;
     }
     default:
