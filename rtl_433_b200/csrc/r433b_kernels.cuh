@@ -105,9 +105,10 @@ struct SliceParams {
 constexpr int kSliceThreads = 128;
 constexpr unsigned kStageWords = 1024; // scratch words per k_slice thread (4 KiB): larger outputs take the second pass
 #ifndef R4_SLICE_CTAS
-#define R4_SLICE_CTAS 12
+#define R4_SLICE_CTAS 8
 #endif
-constexpr int kSliceCtasPerSm = R4_SLICE_CTAS; // 40 registers, 48 warps/SM (measured: 8 -> 13.3 ms, 10 -> 12.4, 12 -> 12.2, 16 -> 13.4)
+constexpr int kSliceCtasPerSm = R4_SLICE_CTAS; // 64 registers, 32 warps/SM.  k_slice2, gated, 4096 x 2^20 cu8: 6 CTAs/SM 7.0 ms, 8 -> 6.3, 12 -> 9.9
+                                               // (40 registers spill); the old k_slice liked 12 (12.6 ms vs 13.4 at 8)
 
 __global__ void __launch_bounds__(kSliceThreads, kSliceCtasPerSm) k_slice(SliceParams p)
 {
