@@ -545,8 +545,12 @@ int r433b_process(r433b_ctx *ctx, r433b_batch const *b)
     // different sizes padded to a common stride): the kernels stop at every stream's own end
     for (uint32_t i = 0; uniform && i < b->n_streams; ++i)
         if (ctx->offsets[i + 1] - ctx->offsets[i] != stride) uniform = false;
-    if (G == 0) // measured on B200 (tools/e2e_sweep.py): many slices of >= 128 KiB per stream beat fewer, larger ones
-        G = (total_bytes >= (256ull << 20) && stride >= (1u << 20)) ? (int)std::min<uint64_t>(r433b_ctx::kMaxGroups, stride / (128u << 10)) : 1;
+    if (G == 0) { // measured on B200 (tools/e2e_sweep.py): many slices of >= 128 KiB per stream beat fewer, larger ones for
+                  // cu8 (4096 streams); cs16 batches (1024 x 4 MiB, FM on: every launch pays the slowest stream's bursts)
+                  // want >= 512 KiB: 8 slices 12.7 GS/s, 16 slices 11.1, 4 slices 11.9
+        uint64_t const min_slice = SS == 4 ? (512u << 10) : (128u << 10);
+        G = (total_bytes >= (256ull << 20) && stride >= (1u << 20)) ? (int)std::min<uint64_t>(r433b_ctx::kMaxGroups, stride / min_slice) : 1;
+    }
     if (b->data_on_device && ctx->pipeline_groups == 0) G = 1; // device input: slices only when asked for
     if (b->want_stages || !n_devs || !uniform || cf32) G = 1;
     uint64_t slice_samples = 0;
