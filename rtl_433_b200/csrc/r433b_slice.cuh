@@ -329,6 +329,19 @@ R4_HD void slicer_advance(PulseView const &p, SlicerState &st, unsigned k)
 
 // ---- set-up: everything the reference does before its main loop; returns false if the slicer
 //      produces nothing (src/pulse_slicer.c, "check for rounding to zero" and early returns)
+// MOD: the modulation as a compile-time constant (kModAny = look at t.modulation).  A warp of k_slice2 runs one device,
+// so slice_dispatch() picks the loop specialised for its slicer: the other front ends, and every Step field that slicer
+// never sets, fold away in slicer_apply().
+constexpr int kModAny = -1;
+template <int MOD>
+R4_HD int slicer_family(SlicerParams const &t)
+{
+    if (MOD != kModAny) return MOD;
+    int const m = t.modulation; // the FSK variants share the front ends of their OOK counterparts
+    return m == kModFskPwm ? (int)kModOokPwm : m == kModFskPcm ? (int)kModOokPcm : m == kModFskMc ? (int)kModOokMc : m;
+}
+
+template <int MOD>
 R4_HD bool slicer_begin0(PulseView const &p, SlicerParams const &t, SlicerState &st)
 {
     st.k = 0;
@@ -337,8 +350,8 @@ R4_HD bool slicer_begin0(PulseView const &p, SlicerParams const &t, SlicerState 
     st.since = 0;
     st.pending = false;
     int const big = 0x7fffffff;
-    switch (t.modulation) {
-    case kModOokPwm: case kModFskPwm: { // src/pulse_slicer.c:369-413; b0..b5 = one/zero/sync lo,hi
+    switch (slicer_family<MOD>(t)) {
+    case kModOokPwm: { // src/pulse_slicer.c:369-413; b0..b5 = one/zero/sync lo,hi
         if (!(t.ok & 1)) return false;
         st.b4 = st.b5 = 0;
         if (t.s_tol > 0) {
@@ -378,7 +391,7 @@ R4_HD bool slicer_begin0(PulseView const &p, SlicerParams const &t, SlicerState 
         }
         return true;
     }
-    case kModOokPcm: case kModFskPcm: { // :89-214, the bit-period estimators
+    case kModOokPcm: { // :89-214, the bit-period estimators
         if (!(t.ok & 1) || t.s_long == 0) return false;
         float f_short = t.f_short, f_long = t.f_long;
         int const gap_limit = t.s_gap ? t.s_gap : t.s_reset;
@@ -451,7 +464,7 @@ R4_HD bool slicer_begin0(PulseView const &p, SlicerParams const &t, SlicerState 
         st.i2 = tol;
         return true;
     }
-    case kModOokMc: case kModFskMc: // :451-478
+    case kModOokMc: // :451-478
         if (!(t.ok & 1)) return false;
         st.edge = dmul((double)t.s_short, 1.5);
         st.i0 = t.s_short - t.s_tol;
@@ -501,14 +514,16 @@ R4_HD bool slicer_begin0(PulseView const &p, SlicerParams const &t, SlicerState 
     }
 }
 
+template <int MOD>
 R4_HD bool slicer_begin(PulseView const &p, SlicerParams const &t, SlicerState &st)
 {
-    if (!slicer_begin0(p, t, st)) return false;
+    if (!slicer_begin0<MOD>(p, t, st)) return false;
     slicer_advance(p, st, st.k); // widths of the first pulse the main loop looks at
     return true;
 }
 
 // ---- one iteration of the main loop of the slicer -> what it does to the bit buffer
+template <int MOD>
 R4_HD Step slicer_step(PulseView const &p, SlicerParams const &t, SlicerState &st)
 {
     Step s;
@@ -518,8 +533,8 @@ R4_HD Step slicer_step(PulseView const &p, SlicerParams const &t, SlicerState &s
     s.emit = kEmitNone;
     s.stop_if_emitted = s.clear_after = false;
     unsigned const n = st.k;
-    switch (t.modulation) {
-    case kModOokPwm: case kModFskPwm: { // src/pulse_slicer.c:415-447
+    switch (slicer_family<MOD>(t)) {
+    case kModOokPwm: { // src/pulse_slicer.c:415-447
         int v = st.cv, g = st.cg;
         if (v > st.b0 && v < st.b1) s.ones = 1;
         else if (v > st.b2 && v < st.b3) s.zeros = 1;
@@ -541,7 +556,7 @@ R4_HD Step slicer_step(PulseView const &p, SlicerParams const &t, SlicerState &s
         slicer_advance(p, st, n + 1);
         break;
     }
-    case kModOokPcm: case kModFskPcm: { // :216-257
+    case kModOokPcm: { // :216-257
         int v = st.cv, g = st.cg;
         int highs = (int)fadd(fmul((float)v, st.f_short), 0.5f);
         int lows = (int)fadd(fmul((float)(g + t.s_short - t.s_long), st.f_long), 0.5f);
@@ -554,7 +569,7 @@ R4_HD Step slicer_step(PulseView const &p, SlicerParams const &t, SlicerState &s
         slicer_advance(p, st, n + 1);
         break;
     }
-    case kModOokMc: case kModFskMc: { // :478-525; the buffer always holds >= 1 row here
+    case kModOokMc: { // :478-525; the buffer always holds >= 1 row here
         if (st.pending) { // bitbuffer_add_bit(&bits, 0) in front of the loop
             st.pending = false;
             s.zeros = 1;
@@ -732,15 +747,29 @@ R4_HD bool slicer_apply(Step const &s, W &w)
     return true;
 }
 
+template <int MOD, class W>
+R4_HD void slice_loop(PulseView const &p, SlicerParams const &t, W &w)
+{
+    SlicerState st;
+    if (!slicer_begin<MOD>(p, t, st)) return;
+    while (st.k < st.total || st.pending) {
+        Step s = slicer_step<MOD>(p, t, st);
+        if (!slicer_apply(s, w)) break;
+    }
+}
+
 template <class W>
 R4_HD void slice_dispatch(PulseView const &p, SlicerParams const &t, W &w)
 {
-    SlicerState st;
-    if (!slicer_begin(p, t, st)) return;
-    while (st.k < st.total || st.pending) {
-        Step s = slicer_step(p, t, st);
-        if (!slicer_apply(s, w)) break;
+    // the four slicers that carry 97 % of the reference's devices get their own loop
+    switch (t.modulation) {
+    case kModOokPwm: case kModFskPwm: slice_loop<kModOokPwm>(p, t, w); return;
+    case kModOokPpm: slice_loop<kModOokPpm>(p, t, w); return;
+    case kModOokPcm: case kModFskPcm: slice_loop<kModOokPcm>(p, t, w); return;
+    case kModOokMc: case kModFskMc: slice_loop<kModOokMc>(p, t, w); return;
+    default: break;
     }
+    slice_loop<kModAny>(p, t, w);
 }
 
 } // namespace r433b

@@ -159,6 +159,8 @@ def decoders_behind_gates_and_threads():
     workers = [refh.Ref(chain_decoders=True, store_bitbuffers=False) for _ in range(4)]
     for w in workers:
         assert w.register_defaults() == n
+    timing = {}
+    import time
     try:
         for mode in ("plain", "gated", "gated+threads"):
             ctx.set_gates(lib.default_gates(devs) if mode != "plain" else None)
@@ -170,10 +172,13 @@ def decoders_behind_gates_and_threads():
                 assert res["n_events"] + res["n_gated"] == plain_events and res["n_gated"] > 2 * res["n_events"]
             if mode != "gated+threads":
                 got_json, got_stats = [], np.zeros((n, 8), np.int64)
+                timing[mode] = 0.0
                 for s in range(len(files)):
                     ptrs = r.L.refh_begin_external_dispatch(r.h)
                     try:
+                        t0 = time.perf_counter()
                         rc = ctx.L.r433b_dispatch_r_devices(ctx.h, C.byref(ctx._res), s, ptrs, n)
+                        timing[mode] += time.perf_counter() - t0
                         assert rc == 0, ctx.L.r433b_last_error(ctx.h)
                         got_json.append([l for l in r.L.refh_json(r.h).decode().split("\n") if l])
                         got_stats += np.array([r.device_stats(i) for i in range(n)], np.int64)
@@ -185,7 +190,9 @@ def decoders_behind_gates_and_threads():
                 for i, w in enumerate(workers):
                     sets[i] = w.L.refh_begin_external_dispatch(w.h)
                 try:
+                    t0 = time.perf_counter()
                     rc = ctx.L.r433b_dispatch_r_devices_parallel(ctx.h, C.byref(ctx._res), sets, n, len(workers))
+                    timing[mode] = time.perf_counter() - t0
                     assert rc == 0, ctx.L.r433b_last_error(ctx.h)
                     got_stats = np.zeros((n, 8), np.int64)
                     per_worker = []
@@ -200,6 +207,19 @@ def decoders_behind_gates_and_threads():
                     assert per_worker[wi] == [l for s in range(wi, len(files), len(workers)) for l in want_json[s]]
             assert np.array_equal(got_stats, want_stats), mode
         assert int(want_stats[:, 0].sum()) > 5000
+        # host-side cost of the replay with the reference's REAL decoders; recorded when the box lets us
+        events = int(want_stats[:, 0].sum())
+        report = {"decode_events": events, "files": len(files),
+                  "seconds": {k: round(v, 4) for k, v in timing.items()},
+                  "decode_events_per_s": {k: round(events / v) for k, v in timing.items() if v > 0},
+                  "what": "r433b_dispatch_r_devices[_parallel] with the unmodified src/devices/*.c decoders (oracle/_ref): "
+                          "plain = every event re-inflated and decoded, gated = events under the length gates booked from "
+                          "their counts, gated+threads = 4 workers with their own decoder sets"}
+        out = os.path.join(os.path.dirname(HERE), "gpurun_out")
+        if os.path.isdir(out):
+            with open(os.path.join(out, "dispatch_real_decoders.json"), "w") as f:
+                json.dump(report, f, indent=1)
+        print("dispatch with real decoders:", report["decode_events_per_s"])
     finally:
         for w in workers:
             w.close()
