@@ -357,7 +357,15 @@ __global__ void __launch_bounds__(kSliceThreads, kSliceCtasPerSm) k_slice2(Slice
                 bool const staged = bytes <= stage_words * 4;
                 if (__all_sync(0xffffffffu, !active || !bytes || staged)) {
                     __syncwarp();
-                    unsigned todo = __ballot_sync(0xffffffffu, active && bytes && fits);
+                    // short outputs (the usual case: a few events of a few words) are copied by their own lane -- the
+                    // lanes' arena regions lie back to back, so neighbouring lanes hit the same lines; only long ones
+                    // are worth a coalesced copy by the whole warp
+                    unsigned const my_words = active && fits ? bytes / 4 : 0;
+                    if (my_words <= 16) {
+                        uint32_t *to = reinterpret_cast<uint32_t *>(p.arena + off);
+                        for (unsigned i = 0; i < my_words; ++i) __stcs(to + i, stage[i]);
+                    }
+                    unsigned todo = __ballot_sync(0xffffffffu, my_words > 16);
                     while (todo) {
                         int const l = __ffs(todo) - 1;
                         todo &= todo - 1;
