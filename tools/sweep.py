@@ -23,8 +23,8 @@ distinct = 8
 devs = lib.default_device_table()
 ctx = lib.Context(0)
 ctx.set_devices(devs)
-print(f"| format | rate | streams x samples | k_detect ms | detect GS/s | detect GB/s | frac of {peak:.0f} GB/s | k_slice ms | packages | events | total GS/s |")
-print("|---|---|---|---|---|---|---|---|---|---|---|")
+print(f"| format | rate | streams x samples | k_front ms | front GB/s (in + out) | frac of {peak:.0f} GB/s | k_detect ms | detect GS/s | detect GB/s (AM in) | frac | k_slice2 ms | packages | events | total GS/s |")
+print("|---|---|---|---|---|---|---|---|---|---|---|---|---|---|")
 for fmt_name, fmt in (("cu8 OOK", lib.FMT_CU8), ("cs16 FSK", lib.FMT_CS16)):
     for rate in (250000, 1024000, 2048000):
         if fmt == lib.FMT_CU8:
@@ -45,13 +45,14 @@ for fmt_name, fmt in (("cu8 OOK", lib.FMT_CU8), ("cs16 FSK", lib.FMT_CS16)):
             for it in range(3):
                 ctx.process(dev.data_ptr(), offsets, fmt, rate, freq, data_on_device=True)
                 tm = ctx.timing()
-                if best is None or tm["detect_ms"] + tm["slice_ms"] < best["detect_ms"] + best["slice_ms"]:
+                if best is None or tm["front_ms"] + tm["detect_ms"] + tm["slice_ms"] < best["front_ms"] + best["detect_ms"] + best["slice_ms"]:
                     best = tm
             c = ctx.counts()
             gsps = c["samples"] / best["detect_ms"] / 1e6
-            gbps = gsps * fmt
-            tot = c["samples"] / (best["detect_ms"] + best["slice_ms"]) / 1e6
-            print(f"| {fmt_name} | {rate / 1e3:.0f}k | {batch} x 2^18 | {best['detect_ms']:.2f} | {gsps:.1f} | {gbps:.1f} | {gbps / peak:.4f} | "
+            gbps = gsps * (2 + 1 / 16)           # k_detect reads the 16-bit AM and the chunk bounds
+            fgb = c["samples"] * (fmt + 2 + 1 / 16) / best["front_ms"] / 1e6  # k_front: IQ in, AM + chunk bounds out
+            tot = c["samples"] / (best["front_ms"] + best["detect_ms"] + best["slice_ms"]) / 1e6
+            print(f"| {fmt_name} | {rate / 1e3:.0f}k | {batch} x 2^18 | {best['front_ms']:.2f} | {fgb:.0f} | {fgb / peak:.3f} | {best['detect_ms']:.2f} | {gsps:.1f} | {gbps:.1f} | {gbps / peak:.4f} | "
                   f"{best['slice_ms']:.2f} | {c['packages']} | {c['events']} | {tot:.1f} |", flush=True)
             del dev
         del small
