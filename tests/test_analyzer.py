@@ -169,3 +169,67 @@ def fnv(bb):
 @needs_ref
 def test_analyzer_matches_the_reference():
     analyzer_matches_the_reference()
+
+
+def edge_cases_of_the_widening_rows():
+    """Empty sets, a package without pulses, gates on loaded packages, call-order errors."""
+    devices = lib.default_device_table()
+    ctx = lib.Context(0)
+    ref = refh.Ref(store_bitbuffers=False)
+    ref.register_defaults()
+    try:
+        ctx.set_devices(devices)
+        ps = lib.Pulses()
+        ctx.process_pulses(ps)  # nothing loaded
+        res = ctx.fetch()
+        assert res["n_packages"] == 0 and res["n_events"] == 0
+        ctx.analyze()
+        empty = np.zeros(1, lib.PULSE_DATA_DTYPE)[0]
+        empty["sample_rate"] = 250000
+        ps.add(empty)  # a pulse_data_t without pulses: the analyzer says so, the slicers emit nothing
+        rng = random.Random(2)
+        full = shaped_package(rng, "ppm")
+        ps.add(full)
+        ctx.set_gates(lib.default_gates(devices))
+        ctx.process_pulses(ps)
+        res = ctx.fetch()
+        assert res["n_packages"] == 2
+        import helpers
+        got = helpers.gpu_stream_results(ctx, 0)
+        want = ref.slice_pulse_data(ctx_pulse_data(ctx, 1))
+        kept = [(e["dev"], e["hash"]) for e in got["events"] if e["package"] == 1]
+        assert not [e for e in got["events"] if e["package"] == 0]
+        gates = lib.default_gates(devices)
+        assert len(kept) + int(res["n_gated"]) == len(want) and res["n_gated"] > 0
+        # the kept events are the reference's events the gates let through, in order
+        it = iter(want)
+        for dev, h in kept:
+            for d2, h2, _bb in it:
+                if (d2, h2) == (dev, h):
+                    break
+            else:
+                raise AssertionError("a stored event is not among the reference's events (in order)")
+        ctx.analyze()
+        a, g, text, bbs = ctx.analysis(0)
+        assert text == "No pulses detected.\n" and g.modulation == 0 and len(bbs) == 0
+        want_text, want_hashes = ref.analyze(ctx_pulse_data(ctx, 1), 1)
+        a, g, text, bbs = ctx.analysis(1)
+        assert text == want_text and [fnv(bb) for bb in bbs] == want_hashes and g.modulation == 5
+        ctx.set_gates(None)
+        # call order: analyze needs a fetched batch
+        x = synth.ook_stream(3, n_samples=1 << 17, n_bursts=1)
+        ctx.process(x, np.array([0, x.nbytes], np.uint64), lib.FMT_CU8, 250000, 433920000)
+        with pytest.raises(lib.R433Error):
+            ctx.analyze()
+        ctx.fetch()
+        ctx.analyze()
+        ps.close()
+    finally:
+        ref.close()
+        ctx.close()
+
+
+@pytest.mark.gpu
+@needs_ref
+def test_edge_cases_of_the_widening_rows():
+    edge_cases_of_the_widening_rows()

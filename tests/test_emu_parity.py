@@ -108,3 +108,8 @@ def test_emu_slice_v1_still_exact(devices):
             "sys.exit(1 if bad or keep!=want or not keep else 0)") % (os.path.dirname(os.path.abspath(__file__)), emu.ROOT)
     env = dict(os.environ, R433B_SLICE_V1="1")
     assert subprocess.call([sys.executable, "-c", code], env=env) == 0
+
+
+@test_analyzer.needs_ref
+def test_emu_edge_cases_of_the_widening_rows():
+    test_analyzer.edge_cases_of_the_widening_rows()
