@@ -1007,14 +1007,17 @@ __device__ R4_NOINLINE int burst_run(WarpSmem &sm, int n)
             // GAP_START (run <= 9 so far) or GAP
             int const cnt = nv_tile - n;
             int const up = det_thresholds(low, h, lv).up;
-            long long lim_a = 10ll * d.longest > 10ll * per_ms ? 10ll * d.longest : 10ll * per_ms;
-            long long const lim_b = 100ll * per_ms;
-            long long const rstar = (lim_a < lim_b ? lim_a : lim_b) + 1; // first run length that ends the package
-            long long je = rstar - run - 1;                               // ... reached at this sample of the scan
+            // min(max(10 * longest, 10 * per_ms), 100 * per_ms) in 32 bits: a pulse of 10 * per_ms samples or more makes
+            // the first limit reach the second, so `longest` can be capped there (per_ms <= 2^31 / 1000: no overflow)
+            int const lim_b = 100 * per_ms;
+            int const lcap = d.longest < 10 * per_ms ? d.longest : 10 * per_ms;
+            int const lim_a = lcap > per_ms ? 10 * lcap : 10 * per_ms;
+            int const rstar = (lim_a < lim_b ? lim_a : lim_b) + 1; // first run length that ends the package
+            int je = rstar - run - 1;                               // ... reached at this sample of the scan
             // the limits are only looked at in GAP, i.e. from the sample after the one that brought the run to 10
-            long long const first_gap = st == kGapStart ? (long long)(kMinPulseSamples - run) : 0;
+            int const first_gap = st == kGapStart ? kMinPulseSamples - run : 0;
             if (je < first_gap) je = first_gap;
-            int const horizon = je < cnt ? (int)je + 1 : cnt; // samples that matter
+            int const horizon = je < cnt ? je + 1 : cnt; // samples that matter
             int ja = 0x7fffffff;
 #pragma unroll 1
             for (int base = 0; base < horizon; base += 32) {
@@ -1047,12 +1050,12 @@ __device__ R4_NOINLINE int burst_run(WarpSmem &sm, int n)
                 continue;
             }
             if (je < cnt) { // end of package by gap length (:443-469)
-                run += (int)je + 1;
+                run += je + 1;
                 put(tr.ook_gap, d.ook_hw, d.ook_n, run);
                 d.ook_n += 1;
                 st = kIdle;
                 pend_type = 1;
-                n += (int)je; // that sample is looked at again in IDLE
+                n += je; // that sample is looked at again in IDLE
                 pend_pos = t0 + (unsigned long long)n;
                 break;
             }
