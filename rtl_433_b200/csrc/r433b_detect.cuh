@@ -24,7 +24,7 @@
 //         (monotone filter: the host proves a1, b0 >= 0, a1 + 2 b0 <= unity; otherwise FM is made for
 //         every window of every tile).
 //       * the carrier estimate g' = g + f/64 - g/64 is DEFERRED after the first pulse: the walk only logs
-//         which samples update it.  When the package ends, g is evaluated over the newest ~1500 logged
+//         which samples update it.  When the package ends, g is evaluated over the newest ~1000 logged
 //         samples from both ends of its range; the recurrence forgets its start at 63/64 per sample, the two
 //         ends meet, and a met pair is the exact value.  If they do not meet (exactly constant input), the
 //         evaluation goes further back, in the end over the whole log from the exactly known value after
@@ -56,7 +56,12 @@ constexpr int kFmPadded = kFmWin + kFmWin / kFmSub; // padded index space: i + i
 constexpr int kWarmFm = 48;                // warm-up samples of the FM trajectories
 constexpr int kFmWindowsPerTile = kTile / kFmWin;
 constexpr unsigned kLogCap = 1024;         // deferred carrier-estimate log: entries per stream
-constexpr int kF1Tail = 1536;              // samples of the first evaluation attempt
+#ifndef R4_F1_TAIL
+#define R4_F1_TAIL 1024
+#endif
+constexpr int kF1Tail = R4_F1_TAIL;        // samples of the first evaluation attempt; when the two ends have not met, the next
+                                           // attempt takes four times as many.  k_detect, 4096 x 2^20 cu8: 768 -> 18.0 ms,
+                                           // 1024 -> 17.7, 1280 -> 18.4, 1536 -> 19.0, 2048 -> 20.2; 640 and less: 20+ (retries)
 
 struct FmJob {
     uint8_t const *src;        // the stream
