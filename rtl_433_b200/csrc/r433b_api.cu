@@ -8,6 +8,7 @@
 #include <chrono>
 #include <cstring>
 #include <atomic>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -53,6 +54,7 @@ struct HostBuf {
 struct r433b_ctx {
     int device = 0;
     std::string err;
+    std::mutex err_mu; // the replay workers of r433b_dispatch_r_devices_parallel() may fail at the same time
     // detector / demod configuration
     int use_mag = 0;
     float level_limit = 0.0f, min_level = -12.1442f, min_snr = 9.0f, fm_low_pass = 0.0f;
@@ -124,6 +126,7 @@ namespace {
 int fail(r433b_ctx *c, int code, char const *what, cudaError_t e = cudaSuccess)
 {
     if (c) {
+        std::lock_guard<std::mutex> lock(c->err_mu);
         c->err = what;
         if (e != cudaSuccess) {
             c->err += ": ";
@@ -1049,7 +1052,7 @@ int r433b_stream_digest(r433b_ctx *ctx, r433b_results const *res, uint32_t strea
             [](r433b_package const &k, uint32_t s) { return k.stream < s; });
     for (r433b_package const *k = begin; k != res->packages + res->n_packages && k->stream == stream; ++k) {
         uint32_t const hdr[] = {k->seq, (uint32_t)k->type, (uint32_t)k->block, (uint32_t)k->offset, (uint32_t)(k->offset >> 32),
-                                (uint32_t)k->end_pos, (uint32_t)(k->end_pos >> 32), k->start_ago, k->end_ago, k->num_pulses,
+                                ctx->pulse_mode ? 0u : (uint32_t)k->end_pos, ctx->pulse_mode ? 0u : (uint32_t)(k->end_pos >> 32), k->start_ago, k->end_ago, k->num_pulses,
                                 k->pulse_count, (uint32_t)k->ook_low_estimate, (uint32_t)k->ook_high_estimate,
                                 (uint32_t)k->fsk_f1_est, (uint32_t)k->fsk_f2_est};
         mix_words(hdr, sizeof(hdr) / 4);
