@@ -233,3 +233,60 @@ def edge_cases_of_the_widening_rows():
 @needs_ref
 def test_edge_cases_of_the_widening_rows():
     edge_cases_of_the_widening_rows()
+
+
+def analyzer_fuzz(n_packages=160, seed=31):
+    """Random pulse trains of every shape the generator knows, plus unstructured ones with few distinct widths (the RfRaw
+    B0 / B1 renderings, repeated groups, more than 32 groups, widths beyond 65535 us): text and trial demodulation
+    against the reference."""
+    rng = random.Random(seed)
+    ref = refh.Ref(store_bitbuffers=False)
+    ctx = lib.Context(0)
+    ctx.set_devices([])
+    try:
+        ps = lib.Pulses()
+        for i in range(n_packages):
+            r = rng.random()
+            rate = rng.choice([250000, 250000, 1000000, 1024000, 48000])
+            if r < 0.5:
+                pd = shaped_package(rng, rng.choice(KINDS), rate)
+            else:
+                pd = np.zeros(1, lib.PULSE_DATA_DTYPE)[0]
+                pd["sample_rate"] = rate
+                n = rng.choice([2, 3, 7, 40, 200, 600, 1200])
+                widths = [rng.choice([3, 10, 37, 120, 500, 2000, 70000]) for _ in range(rng.randrange(1, 5))]
+                gapw = [rng.choice([5, 25, 100, 480, 3000, 20000, 90000]) for _ in range(rng.randrange(1, 6))]
+                for k in range(n):
+                    pd["pulse"][k] = max(0, int(rng.choice(widths) * (1 + rng.uniform(-0.03, 0.03))))
+                    pd["gap"][k] = max(0, int(rng.choice(gapw) * (1 + rng.uniform(-0.03, 0.03))))
+                    if rng.random() < 0.02:
+                        pd["gap"][k] = rng.choice(gapw) * 9
+                pd["num_pulses"] = n
+            if rng.random() < 0.3:
+                pd["fsk_f2_est"], pd["fsk_f1_est"] = rng.randrange(1, 9000), rng.randrange(-9000, 9000)
+            ps.add(pd, stream=i % 3)
+        ctx.process_pulses(ps)
+        res = ctx.fetch()
+        ctx.analyze()
+        seen = set()
+        for i in range(res["n_packages"]):
+            a, g, text, bbs = ctx.analysis(i)
+            if "this can't happen" in text:  # the reference exit(1)s there: the harness would not survive that package
+                continue
+            want_text, want_hashes = ref.analyze(ctx_pulse_data(ctx, i), int(res["packages"][i]["type"]))
+            assert text == want_text, f"package {i}:\n--- reference\n{want_text}\n--- product\n{text}"
+            assert [fnv(bb) for bb in bbs] == want_hashes, f"package {i}"
+            seen.add(int(g.modulation))
+            if "+" in text.split("pdv/#")[-1].split("\n")[0]:
+                seen.add("b0-groups")
+        assert "b0-groups" in seen and len(seen) >= 6
+        ps.close()
+    finally:
+        ref.close()
+        ctx.close()
+
+
+@pytest.mark.gpu
+@needs_ref
+def test_analyzer_fuzz():
+    analyzer_fuzz()

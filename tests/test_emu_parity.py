@@ -113,3 +113,8 @@ def test_emu_slice_v1_still_exact(devices):
 @test_analyzer.needs_ref
 def test_emu_edge_cases_of_the_widening_rows():
     test_analyzer.edge_cases_of_the_widening_rows()
+
+
+@test_analyzer.needs_ref
+def test_emu_analyzer_fuzz():
+    test_analyzer.analyzer_fuzz()

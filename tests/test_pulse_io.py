@@ -141,6 +141,44 @@ def test_ook_and_rfraw_readers_match_the_reference():
     ps.close()
 
 
+def random_ook_text(rng):
+    lines = []
+    for _ in range(rng.randrange(1, 80)):
+        r = rng.random()
+        if r < 0.55:
+            lines.append("%d %d" % (rng.randrange(0, 3000), rng.randrange(0, 30000)))
+        elif r < 0.65:
+            lines.append(rng.choice([";end", ";freq1 %d" % rng.randrange(-50000, 50000), ";freq2 7", ";received @1s", ";", ";ook 3 pulses"]))
+        elif r < 0.78:
+            bins = [rng.randrange(50, 70000) for _ in range(rng.randrange(1, 9))]
+            codes = [rng.choice([0x80, 0x00]) | (rng.randrange(len(bins)) << 4) | rng.randrange(len(bins)) for _ in range(rng.randrange(0, 40))]
+            line = rfraw_b1(bins, codes) if rng.random() < 0.5 else rfraw_b0(bins, codes, rng.randrange(0, 5))
+            if rng.random() < 0.2:
+                line = line[:rng.randrange(4, len(line))]          # truncated
+            if rng.random() < 0.2:
+                line = line.lower().replace("aa", "a a", 1)         # separators, case
+            if rng.random() < 0.15:
+                line += "+" + rfraw_b1([100, 200], [0x81, 0x90])
+            lines.append(line)
+        elif r < 0.88:
+            lines.append("%d%s%d" % (rng.randrange(0, 3000), rng.choice(",;:\t  x"), rng.randrange(-50, 3000)))
+        else:
+            lines.append("".join(rng.choice(" ;-+0123456789abAB\t.") for _ in range(rng.randrange(0, 40))))
+    return rng.choice(["\n", "\r\n"]).join(lines) + rng.choice(["\n", ""])
+
+
+@needs_ref
+def test_ook_reader_random_texts():
+    """400 random pulse texts (rows, headers, whole / truncated / decorated RfRaw lines, junk): the same packages as
+    pulse_data_load() reads out of them."""
+    for seed in range(400):
+        rng = random.Random(1000 + seed)
+        text = random_ook_text(rng)
+        rate = rng.choice(RATES)
+        want = [pd_facts(p) for p in refh.load_ook(text, rate, cap=128)]
+        assert product_load(text, rate) == want, f"seed {seed}: {text!r}"
+
+
 @needs_ref
 def test_writers_match_the_reference():
     rng = random.Random(11)
