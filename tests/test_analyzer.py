@@ -290,3 +290,41 @@ def analyzer_fuzz(n_packages=160, seed=31):
 @needs_ref
 def test_analyzer_fuzz():
     analyzer_fuzz()
+
+
+def analyzer_golden():
+    """tests/golden/analyzer.json (recorded from the reference by tools/make_golden_pulse_io.py): text and trial
+    demodulation without the compiled reference at hand."""
+    import json
+    import os
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "analyzer.json")) as f:
+        cases = json.load(f)["cases"]
+    ctx = lib.Context(0)
+    ctx.set_devices([])
+    try:
+        ps = lib.Pulses()
+        for c in cases:
+            pd = np.zeros(1, lib.PULSE_DATA_DTYPE)[0]
+            pd["sample_rate"] = c["rate"]
+            pd["num_pulses"] = len(c["pulse"])
+            pd["pulse"][:len(c["pulse"])] = c["pulse"]
+            pd["gap"][:len(c["gap"])] = c["gap"]
+            pd["fsk_f1_est"], pd["fsk_f2_est"] = c["fsk_f1_est"], c["fsk_f2_est"]
+            ps.add(pd)
+        ctx.process_pulses(ps)
+        res = ctx.fetch()
+        ctx.analyze()
+        assert res["n_packages"] == len(cases)
+        for i, c in enumerate(cases):
+            assert int(res["packages"][i]["type"]) == c["type"]
+            a, g, text, bbs = ctx.analysis(i)
+            assert text == c["text"], f"{c['kind']} @ {c['rate']}"
+            assert [str(fnv(bb)) for bb in bbs] == c["hashes"], c["kind"]
+        ps.close()
+    finally:
+        ctx.close()
+
+
+@pytest.mark.gpu
+def test_analyzer_golden():
+    analyzer_golden()

@@ -118,3 +118,7 @@ def test_emu_edge_cases_of_the_widening_rows():
 @test_analyzer.needs_ref
 def test_emu_analyzer_fuzz():
     test_analyzer.analyzer_fuzz()
+
+
+def test_emu_analyzer_golden():
+    test_analyzer.analyzer_golden()

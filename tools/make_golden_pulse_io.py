@@ -33,3 +33,28 @@ for i in range(6):
 with open(t.GOLDEN, "w") as f:
     json.dump(out, f, indent=0, separators=(",", ":"))
 print(t.GOLDEN, os.path.getsize(t.GOLDEN), "bytes,", len(out["load"]), "load cases,", len(out["dump"]), "dump cases")
+
+# ---- pulse analyzer: what pulse_analyzer() prints for seeded packages + the hashes of its trial demodulation
+import numpy as np  # noqa: E402
+import test_analyzer as ta  # noqa: E402
+from rtl_433_b200 import lib  # noqa: E402
+
+GOLDEN_AN = os.path.join(os.path.dirname(t.GOLDEN), "analyzer.json")
+rng = random.Random(41)
+ref = refh.Ref(store_bitbuffers=False)
+cases = []
+for rep in range(2):
+    for kind in ta.KINDS:
+        pd = ta.shaped_package(rng, kind, 250000 if rep == 0 else 1024000)
+        pd["ook_low_estimate"] = pd["ook_high_estimate"] = 0  # loaded packages carry no level estimates
+        typ = 2 if (rep == 1 and kind in ("pcm", "pwm_fixed_gap", "manchester")) else 1
+        if typ == 2:
+            pd["fsk_f2_est"], pd["fsk_f1_est"] = 2500, -1800
+        text, hashes = ref.analyze(pd, typ)
+        n = int(pd["num_pulses"])
+        cases.append({"kind": kind, "rate": int(pd["sample_rate"]), "type": typ, "fsk_f1_est": int(pd["fsk_f1_est"]),
+                      "fsk_f2_est": int(pd["fsk_f2_est"]), "pulse": [int(v) for v in pd["pulse"][:n]],
+                      "gap": [int(v) for v in pd["gap"][:n]], "text": text, "hashes": [str(h) for h in hashes]})
+with open(GOLDEN_AN, "w") as f:
+    json.dump({"cases": cases}, f, indent=0, separators=(",", ":"))
+print(GOLDEN_AN, os.path.getsize(GOLDEN_AN), "bytes,", len(cases), "analyzer cases")
